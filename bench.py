@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the SPHERHARM contact hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle; see below)
+
+Workload at N=1: BASELINE.json configs[2] — ~100k polydisperse-shape packing, 8 SH shape types,
+l_max=30, 48x96 surface quadrature, periodic box (the configuration the north_star's single-GPU
+target is quoted on).  A "step" is one full timestep of sh_run (integrate, neighbor decide/build,
+pair kernel, gather, integrate).  `value` = contact-pair evaluations per second with the state
+resident in HBM (device time, CUDA events on the library's stream, max over ranks).  `e2e` = the
+same metric through the Pair::compute-style C-ABI offload with HOST buffers: every step pushes
+x/quat from pinned host memory (sh_put_state), runs sh_compute_forces and reads f/torque back.
+
+Reference arm: the reference (imaranresearch/LAMMPS-SPHERHARM) mount holds only a README, so
+there is no reference binary or package to install or compile; `--impl reference` times this
+repo's CPU oracle (oracle/, kind="port") with all host threads on a bounded sample of the same
+workload.  PARITY/BASELINE UNPINNED — it is the builder's restatement, not LAMMPS+MPI.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import shpkg  # noqa: E402
+
+METRIC = "contact_pair_evals_per_s"
+UNIT = "pair-evals/s"
+
+
+def f_eval(lmax):
+    T = (lmax + 1) * (lmax + 2) // 2
+    return 7 * T + 14 * (lmax + 1) + 40
+
+
+def algorithmic_flops(c, lmax):
+    """flops = 24/transformed node + F_eval(L)/evaluated node + 30/inside node + 200/pair."""
+    return 24.0 * c["nodes_transformed"] + f_eval(lmax) * c["nodes_evaluated"] + 30.0 * c["nodes_inside"] + \
+        200.0 * c["pair_evals"]
+
+
+class ClockSampler:
+    QUERY = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
+            "clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index, self.rows, self._stop, self.t = index, [], threading.Event(), None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self.t = threading.Thread(target=self._loop, daemon=True)
+        self.t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self.t:
+            self.t.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]),
+                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows), "reasons": reasons}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def make_workload(args, pkg, n_particles=None):
+    W = pkg.workloads
+    n = n_particles or args.particles
+    return W.config3_packing(n, lmax=args.lmax, grid=(args.ntheta, args.nphi), seed=30)
+
+
+def cpu_baseline_run(args, pkg, budget_s=20.0, steps=1, warmup=0):
+    """Oracle (CPU port) with all host threads on a bounded sample: a smaller packing of the same kind."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as O
+    cores = os.cpu_count() or 1
+    W = pkg.workloads
+    # probe the pair rate on a tiny sample, then size the bounded sample to the time budget
+    probe = make_workload(args, pkg, 256)
+    o = O.Oracle(threads=cores)
+    W.apply(o, probe)
+    t0 = time.perf_counter()
+    o.compute_forces()
+    tp = time.perf_counter() - t0
+    rate = o.get_counters()["pair_evals"] / max(tp, 1e-9)
+    o.close()
+    per_step = budget_s / max(1, steps + warmup)
+    n_sample = int(min(args.particles, max(256, rate * per_step / 6.0)))
+    cfg = make_workload(args, pkg, n_sample)
+    o = O.Oracle(threads=cores)
+    W.apply(o, cfg)
+    o.compute_forces()       # setup (neighbor list + first force evaluation), untimed like the GPU arm
+    for _ in range(warmup):
+        o.run(1)
+    c0 = o.get_counters()
+    t0 = time.perf_counter()
+    o.run(steps)
+    dt = time.perf_counter() - t0
+    c1 = o.get_counters()
+    pairs = c1["pair_evals"] - c0["pair_evals"]
+    n = len(cfg["x"])
+    o.close()
+    return dict(value=pairs / dt, unit=UNIT, cores=cores, kind="port",
+                sample="%s: %d particles, %d steps, %d pair evals in %.2f s (oracle, OpenMP %d threads); "
+                       "builder's CPU restatement, NOT the reference (LAMMPS+MPI unavailable)"
+                       % (cfg["name"], n, steps, pairs, dt, cores),
+                particle_steps_per_s=n * steps / dt, ms_per_step=1e3 * dt / steps, n_particles=n)
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return 0
+    pkg = shpkg.load()
+    res = cpu_baseline_run(args, pkg, budget_s=120.0, steps=args.steps, warmup=args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, res["n_particles"]),
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "particle_steps_per_s": res["particle_steps_per_s"], "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, n):
+    return {"workload": "BASELINE configs[2]: polydisperse-shape SH packing, 8 shape types, periodic FCC-seeded, "
+                        "packing fraction ~0.55", "n_particles": int(n), "lmax": args.lmax,
+            "quadrature": "%dx%d" % (args.ntheta, args.nphi), "l2_policy": "inputs+node tables re-streamed every step; "
+            "per-step pair/slot buffers (>= 100 MB at 100k) exceed nothing cached between steps is reused by design"}
+
+
+def run_graft(args):
+    rank, world, local = dist_env()
+    pkg = shpkg.load()
+    W = pkg.workloads
+    import torch  # plumbing: device selection, barriers, max-over-ranks
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the SPHERHARM path has no CPU fallback")
+    torch.cuda.set_device(local)
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    # ---- workload: every rank owns an independent replica packing of the same size (weak scaling;
+    # the spatial-decomposition ghost exchange of SURVEY §8e is not built yet — replicas only)
+    cfg = make_workload(args, pkg)
+    n = len(cfg["x"])
+    sim = pkg.ShGpu(device=local)
+    W.apply(sim, cfg)
+    peak = sim.measure_fp64_peak() if rank == 0 else None
+    sim.compute_forces()
+    sim.run(args.warmup)
+    sim.reset_timers()
+
+    def barrier():
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t0 = time.perf_counter()
+    sim.run(args.steps)
+    wall = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    dev_s = sim.get_run_time()["last"]
+    cnt = sim.get_counters()
+    tim = sim.get_timers()
+    pairs_local = cnt["pair_evals"]
+    t_all = torch.tensor([dev_s, wall], dtype=torch.float64, device="cuda")
+    p_all = torch.tensor([float(pairs_local), float(n * args.steps)], dtype=torch.float64, device="cuda")
+    if use_dist:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+        dist.all_reduce(p_all, op=dist.ReduceOp.SUM)
+    dev_s_max, wall_max = t_all.tolist()
+    pairs_total, psteps_total = p_all.tolist()
+
+    # ---- e2e: Pair::compute offload through the C-ABI with pinned HOST buffers, copies inside the timed region
+    st = sim.get_atoms(("x", "quat"))
+    hx = torch.from_numpy(st["x"]).pin_memory()
+    hq = torch.from_numpy(st["quat"]).pin_memory()
+    hf = torch.empty((n, 3), dtype=torch.float64).pin_memory()
+    ht = torch.empty((n, 3), dtype=torch.float64).pin_memory()
+    e2e_steps = max(1, min(args.steps, 20))
+    for _ in range(min(3, args.warmup)):
+        sim.put_state(x=hx.data_ptr(), quat=hq.data_ptr()); sim.compute_forces(); sim.get_forces(hf.data_ptr(), ht.data_ptr())
+    c0 = sim.get_counters()["pair_evals"]
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        hx[:, 0] += 1e-9  # the host code owns and mutates the positions between calls
+        sim.put_state(x=hx.data_ptr(), quat=hq.data_ptr())
+        sim.compute_forces()
+        sim.get_forces(hf.data_ptr(), ht.data_ptr())
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_pairs = sim.get_counters()["pair_evals"] - c0
+    e_all = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    ep_all = torch.tensor([float(e2e_pairs)], dtype=torch.float64, device="cuda")
+    if use_dist:
+        dist.all_reduce(e_all, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ep_all, op=dist.ReduceOp.SUM)
+
+    if rank == 0:
+        flops = algorithmic_flops(cnt, args.lmax)
+        pair_s = tim["seconds_pair"]
+        achieved = flops / max(pair_s, 1e-12) / 1e12
+        peak_tf = peak["flops_per_s"] / 1e12
+        # FP64 pipe slots: 12/transformed node + I_eval/evaluated node
+        T = (args.lmax + 1) * (args.lmax + 2) // 2
+        slots = 12.0 * cnt["nodes_transformed"] + (4 * T + 10 * (args.lmax + 1) + 30) * cnt["nodes_evaluated"] + 15.0 * cnt["nodes_inside"]
+        roofline = {"bound": "fp64", "kernel": "pair_kernel", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": achieved / peak_tf, "traffic": None,
+                    "peak_source": "K0 DFMA microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 entry); "
+                                   "nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2 TFLOP/s",
+                    "frac_of_nominal": achieved / 37.2,
+                    "pipe_slot_frac": slots * 2.0 / max(pair_s, 1e-12) / peak["flops_per_s"],
+                    "avg_launch_ms": 1e3 * pair_s / max(1, tim["pair_launches"]),
+                    "flops_per_launch": flops / max(1, tim["pair_launches"]),
+                    "pair_kernel_share_of_step": pair_s / max(dev_s, 1e-12),
+                    "evaluated_nodes_per_pair": cnt["nodes_evaluated"] / max(1, cnt["pair_evals"]),
+                    "inside_nodes_per_pair": cnt["nodes_inside"] / max(1, cnt["pair_evals"])}
+        cpu = cpu_baseline_run(args, pkg, budget_s=args.cpu_budget, steps=1, warmup=0) if (world == 1 and not args.no_cpu) else None
+        line = {"metric": METRIC, "value": pairs_total / dev_s_max, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * dev_s_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(args, n),
+                "particle_steps_per_s": psteps_total / dev_s_max,
+                "wall_ms_per_step": 1e3 * wall_max / args.steps,
+                "neighbor_builds": cnt["neighbor_builds"],
+                "clocks": clocks,
+                "e2e": {"value": ep_all.item() / e_all.item(), "unit": UNIT, "h2d_bytes_per_step": int(n * 7 * 8),
+                        "d2h_bytes_per_step": int(n * 6 * 8), "steps": e2e_steps,
+                        "path": "sh_put_state(x,quat pinned host) + sh_compute_forces + sh_get_forces(f,torque pinned host)"},
+                "gpu_launches": int(cnt["kernel_launches"]),
+                "roofline": roofline}
+        if cpu:
+            line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    sim.close()
+    if use_dist:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
+    ap.add_argument("--particles", type=int, default=100000)
+    ap.add_argument("--lmax", type=int, default=30)
+    ap.add_argument("--ntheta", type=int, default=48)
+    ap.add_argument("--nphi", type=int, default=96)
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "graft":
+        args.warmup = 3
+    return run_reference(args) if args.impl == "reference" else run_graft(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,100 @@
+/* shgpu.h — C ABI of the B200-native SPHERHARM contact hot path (libshgpu.so).
+ *
+ * What each entry point replaces.  The reference is imaranresearch/LAMMPS-SPHERHARM; the mount
+ * /root/reference contains only README.md:1-3 (the heading "SPHERHARM Package to simulate complex
+ * shaped granular particles"), so no reference file:line exists to cite beyond that.  The
+ * interfaces named below are the LAMMPS style interfaces that BASELINE.json:5 (north_star) says the
+ * path sits behind ("atom_style spherharm, pair_style/pair_coeff spherharm, fix nve/sh-style
+ * quaternion integrator, wall fixes"); see SURVEY.md §8(b) and INTEGRATION.md for the binding a
+ * LAMMPS maintainer would add on the reference side.
+ *
+ * Conventions: every call returns int (0 = OK, <0 = error; text via sh_last_error).  No C++
+ * exception crosses the boundary.  The handle is opaque, owned by the library and not thread-safe
+ * (one host thread drives one handle, bound to one CUDA device).  Host arrays passed in are copied;
+ * arrays passed out are filled into caller-owned buffers of the stated length (NULL = skip).
+ * Reals are double, indices int32, tags int64.  Per-atom vectors are AoS rows (n x 3, quaternion
+ * n x 4 as w,x,y,z).  There is NO CPU fallback: without a usable CUDA device sh_create fails.
+ */
+#ifndef SHGPU_H
+#define SHGPU_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sh_ctx sh_ctx;
+
+/* lifecycle ------------------------------------------------------------------------------- */
+int sh_create(sh_ctx **h, int device_id);           /* LAMMPS::LAMMPS + package init            */
+int sh_destroy(sh_ctx *h);
+const char *sh_last_error(const sh_ctx *h);         /* Error::all(FLERR,msg) text               */
+int sh_version(void);
+
+/* domain (input: boundary / region / create_box) ---------------------------------------------- */
+int sh_set_box(sh_ctx *h, const double lo[3], const double hi[3], const int periodic[3]);
+
+/* atom_style spherharm <lmax> <quadrature> <shape files>  (AtomVec::process_args) ------------- */
+int sh_set_quadrature(sh_ctx *h, int n_theta, int n_phi);   /* Gauss-Legendre x uniform-phi     */
+int sh_add_shape(sh_ctx *h, int lmax, const double *a_lm, const double *b_lm, double density,
+                 int *shape_id_out);                /* a/b index l(l+1)/2+m, real orthonormal SH */
+int sh_get_shape_props(const sh_ctx *h, int shape, double *volume, double com[3],
+                       double inertia[3], double quat_principal[4], double *rmax, double *rmin);
+int sh_get_nodes(const sh_ctx *h, int shape, double *p /*nq x 3*/, double *nds /*nq x 3*/);
+
+/* create_atoms / read_data / set quat  (AtomVec::data_atom, create_atom) ---------------------- */
+int sh_set_atoms(sh_ctx *h, int64_t n, const int64_t *tag, const int *shape, const double *x,
+                 const double *v, const double *quat, const double *angmom);
+
+/* pair_style spherharm / pair_coeff i j k exponent  (Pair::settings, Pair::coeff) -------------- */
+int sh_pair_coeff(sh_ctx *h, int shape_i, int shape_j, double k, double exponent);
+/* fix wall for SH particles (Fix::post_force): plane through point, normal into the domain -- */
+int sh_add_wall(sh_ctx *h, const double point[3], const double normal[3], double k,
+                double exponent);
+/* fix gravity --------------------------------------------------------------------------------- */
+int sh_set_gravity(sh_ctx *h, const double g[3]);
+/* neighbor <skin> bin / neigh_modify every N check yes|no ------------------------------------- */
+int sh_set_neighbor(sh_ctx *h, double skin, int every, int check);
+/* timestep ------------------------------------------------------------------------------------- */
+int sh_set_timestep(sh_ctx *h, double dt);
+
+/* run N  (Verlet::setup + Verlet::run: fix nve/sh initial_integrate, neighbor decide/build,
+ * Pair::compute, wall post_force, final_integrate) -------------------------------------------- */
+int sh_run(sh_ctx *h, int64_t nsteps);
+/* one Pair::compute + wall post_force on the current state (run 0) ---------------------------- */
+int sh_compute_forces(sh_ctx *h);
+
+/* Pair::compute-style offload for a host code that owns the atoms (the drop-in a LAMMPS pair style
+ * wrapper uses every step): push x / quat (v, angmom optional; NULL = keep), sh_compute_forces,
+ * then read f / torque.  The neighbor list is kept across calls and rebuilt when the skin is
+ * exhausted.  Host pointers may be pageable or pinned. ------------------------------------------ */
+int sh_put_state(sh_ctx *h, int64_t n, const double *x, const double *v, const double *quat,
+                 const double *angmom);
+int sh_get_forces(const sh_ctx *h, int64_t n, double *f, double *torque);
+
+/* state read-back (dump / thermo / compute) ---------------------------------------------------- */
+int sh_get_natoms(const sh_ctx *h, int64_t *n);
+int sh_get_atoms(const sh_ctx *h, int64_t n, double *x, double *v, double *quat, double *angmom,
+                 double *f, double *torque);         /* in sh_set_atoms order                    */
+int sh_get_pairs(const sh_ctx *h, int64_t cap, int64_t *npairs, int64_t *tag_i, int64_t *tag_j,
+                 double *V, double *F, double *tau_i, double *tau_j, double *centroid);
+int sh_get_energy(const sh_ctx *h, double *ke_trans, double *ke_rot, double *e_contact);
+int sh_get_counters(const sh_ctx *h, int64_t *pair_evals, int64_t *nodes_transformed,
+                    int64_t *nodes_evaluated, int64_t *nodes_inside, int64_t *neighbor_builds,
+                    int64_t *kernel_launches);
+/* device time (CUDA events on the library's stream) accumulated since sh_reset_timers ---------- */
+int sh_get_timers(const sh_ctx *h, double *seconds_pair, int64_t *pair_launches,
+                  double *seconds_neigh, double *seconds_other);
+int sh_reset_timers(sh_ctx *h);
+/* device time of sh_run (events on the library's stream bracketing all steps of the call) -------- */
+int sh_get_run_time(const sh_ctx *h, double *seconds_last_run, double *seconds_total);
+
+/* tuning knobs of the pair kernel (block size, CTAs per SM); 0 = default ---------------------- */
+int sh_set_pair_tuning(sh_ctx *h, int threads_per_cta, int ctas_per_sm, int variant);
+
+/* FP64 FMA-pipe peak microbenchmark (K0): returns measured DFMA flop/s of the device ----------- */
+int sh_measure_fp64_peak(sh_ctx *h, double *flops_per_s, double *sm_clock_mhz_est);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

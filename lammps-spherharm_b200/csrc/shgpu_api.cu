@@ -1,0 +1,788 @@
+// shgpu_api.cu — context, step driver and extern "C" boundary of libshgpu.so (include/shgpu.h).
+//
+// Host-side step driver = the Verlet::setup / Verlet::run frame of SURVEY §3.1 restricted to the
+// SPHERHARM path: integrate_initial -> (neighbor decide/build) -> pair -> wall -> gather ->
+// integrate_final, all on one CUDA stream.  There is no CPU compute path: every force, torque,
+// neighbor list and integration step is produced by the kernels in this directory.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/shgpu.h"
+#include "neighbor_kernels.cuh"
+#include "pair_kernel.cuh"
+#include "shape_tables.h"
+#include "step_kernels.cuh"
+
+using namespace shgpu;
+
+namespace {
+
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t cap = 0;
+  void ensure(size_t n) {
+    if (n <= cap) return;
+    if (p) cudaFree(p);
+    size_t want = std::max<size_t>(n, cap + cap / 2);
+    if (cudaMalloc(&p, want * sizeof(T)) != cudaSuccess) { p = nullptr; cap = 0; throw std::string("cudaMalloc failed"); }
+    cap = want;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct ShapeDev {
+  DevBuf<double> Ap, node;   // node: 6 x nq
+  DevBuf<double2> ab;
+};
+
+}  // namespace
+
+struct sh_ctx {
+  std::string err;
+  int device = 0, sm_count = 148;
+  cudaStream_t stream = nullptr;
+  // domain
+  double lo[3] = {-1e30, -1e30, -1e30}, hi[3] = {1e30, 1e30, 1e30};
+  int periodic[3] = {0, 0, 0};
+  bool box_set = false;
+  // shapes
+  int n_theta = 32, n_phi = 64;
+  std::vector<ShapeTables> shapes;
+  std::vector<ShapeDev> shape_dev;
+  std::vector<DevShape> shape_host_view;
+  DevBuf<DevShape> d_shapes;
+  bool shapes_dirty = true;
+  std::vector<double> pk, pm;  // SH_MAX_SHAPES^2
+  DevBuf<double> d_pk, d_pm;
+  bool coeff_dirty = true;
+  WallSet walls{};
+  double g[3] = {0, 0, 0}, skin = 0.0, dt = 1e-4;
+  int neigh_every = 1, neigh_check = 1;
+  // atoms
+  int64_t n = 0;
+  int stride = 0;
+  DevBuf<double> x, v, q, L, f, tq, c, Rs, c0, wallf, ewall, ke;
+  DevBuf<int> shape;
+  std::vector<int64_t> tag;
+  // neighbor
+  DevBuf<int> cell_of, cell_count, cell_start, cell_fill, cell_atoms, tile_sum, cnt_full, cnt_half, nbr_off, half_off,
+      nbr_j, pair_i, pair_j, pair_eij, pair_eji, scalars;  // scalars: [0]=total [1]=rebuild flag [2]=work counter
+  DevBuf<double> bbox, slot, pres, stage;
+  DevBuf<unsigned long long> counters;
+  int npairs = 0, nentries = 0;
+  int slot_stride = 0, pres_stride = 0;
+  int *h_pinned = nullptr;  // [0] total/flag scratch
+  bool forces_valid = false, list_valid = false;
+  int64_t steps_since_build = 0;
+  // stats
+  int64_t neighbor_builds = 0, kernel_launches = 0;
+  std::vector<cudaEvent_t> ev;  // pairs of (start,stop) for the pair kernel
+  size_t ev_used = 0;
+  double sec_pair = 0, sec_neigh = 0, sec_other = 0, sec_run_last = 0, sec_run_total = 0;
+  cudaEvent_t run_e0 = nullptr, run_e1 = nullptr;
+  int64_t pair_launches = 0;
+  // tuning
+  int tune_threads = 0, tune_ctas_per_sm = 0, tune_variant = 0;
+};
+
+namespace {
+
+int fail(sh_ctx *h, const std::string &m) { h->err = m; return -1; }
+int cuda_fail(sh_ctx *h, const char *where, cudaError_t e) {
+  h->err = std::string(where) + ": " + cudaGetErrorString(e);
+  return -2;
+}
+#define CU(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return cuda_fail(h, #call, _e); } while (0)
+
+inline int cdiv(int64_t a, int b) { return (int)((a + b - 1) / b); }
+
+AtomView view(sh_ctx *h) {
+  AtomView A;
+  A.x = h->x.p; A.v = h->v.p; A.q = h->q.p; A.L = h->L.p; A.f = h->f.p; A.tq = h->tq.p;
+  A.c = h->c.p; A.Rs = h->Rs.p; A.c0 = h->c0.p; A.wallf = h->wallf.p; A.shape = h->shape.p;
+  A.n = (int)h->n; A.stride = h->stride;
+  return A;
+}
+
+int upload_shapes(sh_ctx *h) {
+  if (!h->shapes_dirty) return 0;
+  const int ns = (int)h->shapes.size();
+  h->shape_dev.resize(ns);
+  h->shape_host_view.resize(ns);
+  try {
+    for (int s = 0; s < ns; s++) {
+      const ShapeTables &t = h->shapes[s];
+      ShapeDev &d = h->shape_dev[s];
+      if (d.Ap.p) continue;  // already uploaded
+      d.Ap.ensure(t.nterms); d.ab.ensure(t.nterms); d.node.ensure((size_t)6 * t.nq);
+      std::vector<double2> ab(t.nterms);
+      for (int k = 0; k < t.nterms; k++) ab[k] = make_double2(t.ah[k], t.bh[k]);
+      CU(cudaMemcpy(d.Ap.p, t.Ap.data(), t.nterms * sizeof(double), cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(d.ab.p, ab.data(), t.nterms * sizeof(double2), cudaMemcpyHostToDevice));
+      for (int e = 0; e < 3; e++) {
+        CU(cudaMemcpy(d.node.p + (size_t)e * t.nq, t.node_p[e].data(), t.nq * sizeof(double), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d.node.p + (size_t)(3 + e) * t.nq, t.node_n[e].data(), t.nq * sizeof(double), cudaMemcpyHostToDevice));
+      }
+      DevShape &v = h->shape_host_view[s];
+      v.lmax = t.lmax; v.nterms = t.nterms; v.nq = t.nq; v.nchunks = (t.nq + 31) / 32;
+      v.rmax = t.rmax; v.rmin = t.rmin; v.rmax2 = t.rmax * t.rmax; v.rmin2 = t.rmin * t.rmin;
+      v.mass = t.mass; v.inv_mass = 1.0 / t.mass;
+      for (int e = 0; e < 3; e++) { v.inertia[e] = t.inertia[e]; v.com[e] = t.com[e]; }
+      for (int r = 0; r < 3; r++) for (int cidx = 0; cidx < 3; cidx++) v.Rp[3 * r + cidx] = t.Rp[r][cidx];
+      v.Ap = d.Ap.p; v.ab = d.ab.p;
+      v.px = d.node.p; v.py = d.node.p + t.nq; v.pz = d.node.p + 2 * (size_t)t.nq;
+      v.nx = d.node.p + 3 * (size_t)t.nq; v.ny = d.node.p + 4 * (size_t)t.nq; v.nz = d.node.p + 5 * (size_t)t.nq;
+    }
+    h->d_shapes.ensure(std::max(ns, 1));
+  } catch (std::string &e) { return fail(h, e); }
+  if (ns) CU(cudaMemcpy(h->d_shapes.p, h->shape_host_view.data(), ns * sizeof(DevShape), cudaMemcpyHostToDevice));
+  h->shapes_dirty = false;
+  return 0;
+}
+
+int upload_coeffs(sh_ctx *h) {
+  if (!h->coeff_dirty) return 0;
+  try { h->d_pk.ensure(SH_MAX_SHAPES * SH_MAX_SHAPES); h->d_pm.ensure(SH_MAX_SHAPES * SH_MAX_SHAPES); }
+  catch (std::string &e) { return fail(h, e); }
+  CU(cudaMemcpy(h->d_pk.p, h->pk.data(), h->pk.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_pm.p, h->pm.data(), h->pm.size() * sizeof(double), cudaMemcpyHostToDevice));
+  h->coeff_dirty = false;
+  return 0;
+}
+
+// exclusive scan of in[0..n) into out[0..n], out[n] = total; returns total through *total_host
+int exclusive_scan(sh_ctx *h, const int *in, int *out, int n, int *total_host) {
+  const int ntiles = std::max(1, cdiv(n, SCAN_TILE));
+  try { h->tile_sum.ensure(ntiles); } catch (std::string &e) { return fail(h, e); }
+  int *d_total = h->scalars.p;
+  scan_tile_kernel<<<ntiles, SCAN_THREADS, 0, h->stream>>>(in, out, h->tile_sum.p, n);
+  scan_sums_kernel<<<1, 1024, 0, h->stream>>>(h->tile_sum.p, ntiles, d_total);
+  scan_add_kernel<<<std::max(1, cdiv(n, 256)), 256, 0, h->stream>>>(out, h->tile_sum.p, n, d_total);
+  h->kernel_launches += 3;
+  if (total_host) {
+    CU(cudaMemcpyAsync(h->h_pinned, d_total, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    *total_host = h->h_pinned[0];
+  }
+  return 0;
+}
+
+int build_neighbors(sh_ctx *h) {
+  const int n = (int)h->n, st = h->stride;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0, h->stream));
+  CU(cudaMemsetAsync(h->scalars.p + 1, 0, sizeof(int), h->stream));  // displacement flag
+  double rmaxg = 0;
+  for (auto &s : h->shapes) rmaxg = std::max(rmaxg, s.rmax);
+  const double cut = 2.0 * rmaxg + h->skin;
+  BinGrid G;
+  G.skin = h->skin;
+  bool need_bbox = false;
+  for (int d = 0; d < 3; d++) {
+    G.periodic[d] = h->periodic[d];
+    G.boxlen[d] = h->hi[d] - h->lo[d];
+    if (h->periodic[d]) {
+      if (G.boxlen[d] < 2.0 * cut) return fail(h, "periodic box shorter than 2x cutoff");
+    } else need_bbox = true;
+  }
+  double bmin[3] = {0, 0, 0}, bmax[3] = {0, 0, 0};
+  if (need_bbox && n > 0) {
+    auto enc = [](double v) { long long b; std::memcpy(&b, &v, 8); return b >= 0 ? b : (b ^ 0x7fffffffffffffffLL); };
+    auto dec = [](long long b) { long long u = b >= 0 ? b : (b ^ 0x7fffffffffffffffLL); double v; std::memcpy(&v, &u, 8); return v; };
+    long long init[6];
+    for (int d = 0; d < 3; d++) { init[d] = enc(1e300); init[3 + d] = enc(-1e300); }
+    CU(cudaMemcpyAsync(h->bbox.p, init, sizeof init, cudaMemcpyHostToDevice, h->stream));
+    bbox_kernel<<<std::min(1024, cdiv(n, 256)), 256, 0, h->stream>>>(h->c.p, n, st, h->bbox.p);
+    h->kernel_launches++;
+    long long out[6];
+    CU(cudaMemcpyAsync(out, h->bbox.p, sizeof out, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int d = 0; d < 3; d++) { bmin[d] = dec(out[d]); bmax[d] = dec(out[3 + d]); }
+    for (int d = 0; d < 3; d++) if (!std::isfinite(bmin[d]) || !std::isfinite(bmax[d])) return fail(h, "non-finite atom coordinates");
+  }
+  int64_t ncell = 1;
+  for (int d = 0; d < 3; d++) {
+    if (h->periodic[d]) { G.lo[d] = h->lo[d]; G.len[d] = G.boxlen[d]; }
+    else { G.lo[d] = bmin[d]; G.len[d] = (bmax[d] - bmin[d]) * (1.0 + 1e-9) + 1e-9; }
+    int nc = (int)std::floor(G.len[d] / cut);
+    nc = std::max(1, std::min(nc, 1024));
+    if (h->periodic[d] && nc < 3) nc = 1;
+    G.nc[d] = nc;
+    ncell *= nc;
+  }
+  // limit the grid to a few cells per atom (sparse, spread-out systems)
+  while (ncell > std::max<int64_t>(4096, 8 * (int64_t)n)) {
+    int dmax = 0;
+    for (int d = 1; d < 3; d++) if (G.nc[d] > G.nc[dmax]) dmax = d;
+    ncell /= G.nc[dmax];
+    G.nc[dmax] = std::max(1, G.nc[dmax] / 2);
+    if (h->periodic[dmax] && G.nc[dmax] < 3) G.nc[dmax] = 1;
+    ncell *= G.nc[dmax];
+  }
+  try {
+    h->cell_of.ensure(n + 1); h->cell_count.ensure(ncell + 1); h->cell_start.ensure(ncell + 2); h->cell_fill.ensure(ncell + 1);
+    h->cell_atoms.ensure(n + 1); h->cnt_full.ensure(n + 1); h->cnt_half.ensure(n + 1); h->nbr_off.ensure(n + 2); h->half_off.ensure(n + 2);
+  } catch (std::string &e) { return fail(h, e); }
+  const int nb = std::max(1, cdiv(n, 256));
+  CU(cudaMemsetAsync(h->cell_count.p, 0, (ncell + 1) * sizeof(int), h->stream));
+  CU(cudaMemsetAsync(h->cell_fill.p, 0, (ncell + 1) * sizeof(int), h->stream));
+  bin_count_kernel<<<nb, 256, 0, h->stream>>>(h->c.p, n, st, G, h->cell_of.p, h->cell_count.p);
+  if (exclusive_scan(h, h->cell_count.p, h->cell_start.p, (int)ncell, nullptr)) return -1;
+  bin_fill_kernel<<<nb, 256, 0, h->stream>>>(n, h->cell_of.p, h->cell_start.p, h->cell_fill.p, h->cell_atoms.p);
+  bin_sort_kernel<<<cdiv(ncell, 256), 256, 0, h->stream>>>((int)ncell, h->cell_start.p, h->cell_atoms.p);
+  nbr_count_kernel<<<nb, 256, 0, h->stream>>>(h->c.p, h->shape.p, h->d_shapes.p, n, st, G, h->cell_of.p, h->cell_start.p,
+                                              h->cell_atoms.p, h->cnt_full.p, h->cnt_half.p);
+  h->kernel_launches += 4;
+  int nentries = 0, npairs = 0;
+  if (exclusive_scan(h, h->cnt_full.p, h->nbr_off.p, n, &nentries)) return -1;
+  if (exclusive_scan(h, h->cnt_half.p, h->half_off.p, n, &npairs)) return -1;
+  try {
+    h->nbr_j.ensure(nentries + 1); h->pair_i.ensure(npairs + 1); h->pair_j.ensure(npairs + 1);
+    h->pair_eij.ensure(npairs + 1); h->pair_eji.ensure(npairs + 1);
+    if ((size_t)nentries + 1 > (size_t)h->slot_stride) { h->slot_stride = (int)((nentries + 1) * 1.25) + 64; h->slot.release(); h->slot.ensure((size_t)6 * h->slot_stride); }
+    if ((size_t)npairs + 1 > (size_t)h->pres_stride) { h->pres_stride = (int)((npairs + 1) * 1.25) + 64; h->pres.release(); h->pres.ensure((size_t)14 * h->pres_stride); }
+  } catch (std::string &e) { return fail(h, e); }
+  nbr_fill_kernel<<<nb, 256, 0, h->stream>>>(h->c.p, h->shape.p, h->d_shapes.p, n, st, G, h->cell_of.p, h->cell_start.p,
+                                             h->cell_atoms.p, h->nbr_off.p, h->half_off.p, h->nbr_j.p, h->pair_i.p,
+                                             h->pair_j.p, h->pair_eij.p);
+  pair_reverse_kernel<<<std::max(1, cdiv(npairs, 256)), 256, 0, h->stream>>>(npairs, h->pair_i.p, h->pair_j.p, h->nbr_off.p,
+                                                                             h->nbr_j.p, h->pair_eji.p);
+  copy_origin_kernel<<<nb, 256, 0, h->stream>>>(h->c.p, h->c0.p, n, st);
+  h->kernel_launches += 3;
+  CU(cudaEventRecord(e1, h->stream));
+  CU(cudaEventSynchronize(e1));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  h->sec_neigh += ms * 1e-3;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  CU(cudaGetLastError());
+  h->npairs = npairs; h->nentries = nentries;
+  h->list_valid = true; h->steps_since_build = 0; h->neighbor_builds++;
+  return 0;
+}
+
+int drain_events(sh_ctx *h) {
+  if (h->ev_used == 0) return 0;
+  CU(cudaStreamSynchronize(h->stream));
+  for (size_t k = 0; k + 1 < h->ev_used; k += 2) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev[k], h->ev[k + 1]);
+    h->sec_pair += ms * 1e-3;
+  }
+  h->ev_used = 0;
+  return 0;
+}
+
+template <int NT>
+int launch_pair(sh_ctx *h, const PairArgs &A, int ctas_per_sm, size_t smem) {
+  CU(cudaFuncSetAttribute(pair_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+  int occ = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pair_kernel<NT>, NT, smem));
+  if (occ < 1) return fail(h, "pair kernel does not fit on an SM (shared memory)");
+  if (ctas_per_sm > 0) occ = std::min(occ, ctas_per_sm);
+  const int grid = std::max(1, std::min(A.npairs, occ * h->sm_count));
+  pair_kernel<NT><<<grid, NT, smem, h->stream>>>(A);
+  return 0;
+}
+
+int compute_forces_device(sh_ctx *h) {
+  const int n = (int)h->n;
+  if (n == 0) { h->forces_valid = true; return 0; }
+  AtomView A = view(h);
+  const int nb = cdiv(n, 256);
+  if (h->npairs > 0) {
+    PairArgs P;
+    P.shapes = h->d_shapes.p; P.c = h->c.p; P.Rs = h->Rs.p; P.x = h->x.p; P.shape = h->shape.p; P.stride = h->stride;
+    P.pair_i = h->pair_i.p; P.pair_j = h->pair_j.p; P.pair_eij = h->pair_eij.p; P.pair_eji = h->pair_eji.p;
+    P.npairs = h->npairs; P.slot = h->slot.p; P.slot_stride = h->slot_stride; P.pres = h->pres.p; P.pres_stride = h->pres_stride;
+    P.pk = h->d_pk.p; P.pm = h->d_pm.p;
+    for (int d = 0; d < 3; d++) { P.boxlen[d] = h->hi[d] - h->lo[d]; P.periodic[d] = h->periodic[d]; }
+    P.work_counter = h->scalars.p + 2; P.counters = h->counters.p;
+    int maxT = 1, maxq = 32;
+    for (auto &s : h->shapes) { maxT = std::max(maxT, s.nterms); maxq = std::max(maxq, s.nq); }
+    P.max_terms = maxT; P.max_nq = maxq;
+    CU(cudaMemsetAsync(h->scalars.p + 2, 0, sizeof(int), h->stream));
+    int nt = h->tune_threads ? h->tune_threads : 128;
+    if (h->ev_used + 2 > h->ev.size()) { if (drain_events(h)) return -2; }
+    CU(cudaEventRecord(h->ev[h->ev_used], h->stream));
+    int rc;
+    if (nt == 256) rc = launch_pair<256>(h, P, h->tune_ctas_per_sm, pair_smem_bytes(maxT, maxq, 8));
+    else if (nt == 64) rc = launch_pair<64>(h, P, h->tune_ctas_per_sm, pair_smem_bytes(maxT, maxq, 2));
+    else rc = launch_pair<128>(h, P, h->tune_ctas_per_sm, pair_smem_bytes(maxT, maxq, 4));
+    if (rc) return rc;
+    CU(cudaEventRecord(h->ev[h->ev_used + 1], h->stream));
+    h->ev_used += 2;
+    h->pair_launches++; h->kernel_launches++;
+  }
+  if (h->walls.n > 0) {
+    wall_kernel<<<cdiv((int64_t)n * 32, 256), 256, 0, h->stream>>>(A, h->d_shapes.p, h->walls, h->ewall.p);
+    h->kernel_launches++;
+  }
+  gather_kernel<<<nb, 256, 0, h->stream>>>(A, h->nbr_off.p, h->slot.p, h->slot_stride, h->walls.n > 0);
+  h->kernel_launches++;
+  CU(cudaGetLastError());
+  h->forces_valid = true;
+  return 0;
+}
+
+int prepare(sh_ctx *h) {
+  if (h->n > 0 && h->shapes.empty()) return fail(h, "no shapes defined");
+  int rc;
+  if ((rc = upload_shapes(h))) return rc;
+  if ((rc = upload_coeffs(h))) return rc;
+  return 0;
+}
+
+int setup_forces(sh_ctx *h) {
+  int rc;
+  if ((rc = prepare(h))) return rc;
+  if (h->n > 0) {
+    const double trig = 0.5 * h->skin;
+    pose_kernel<<<cdiv(h->n, 256), 256, 0, h->stream>>>(view(h), h->d_shapes.p, h->list_valid ? trig * trig : -1.0, h->scalars.p + 1);
+    h->kernel_launches++;
+    bool rebuild = !h->list_valid;
+    if (!rebuild) {
+      CU(cudaMemcpyAsync(h->h_pinned + 4, h->scalars.p + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+      rebuild = h->h_pinned[4] != 0;
+    }
+    if (rebuild) { if ((rc = build_neighbors(h))) return rc; }
+  }
+  return compute_forces_device(h);
+}
+
+}  // namespace
+
+// =====================================================================================
+extern "C" {
+
+int sh_version(void) { return 100; }
+
+int sh_create(sh_ctx **out, int device_id) {
+  if (!out) return -1;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return -3;  // no CUDA device: no fallback
+  if (device_id < 0 || device_id >= ndev) return -4;
+  sh_ctx *h = new sh_ctx();
+  h->device = device_id;
+  if (cudaSetDevice(device_id) != cudaSuccess) { delete h; return -5; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device_id);
+  h->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return -6; }
+  h->pk.assign(SH_MAX_SHAPES * SH_MAX_SHAPES, 1.0);
+  h->pm.assign(SH_MAX_SHAPES * SH_MAX_SHAPES, 1.0);
+  try {
+    h->scalars.ensure(16); h->bbox.ensure(8); h->counters.ensure(8);
+  } catch (std::string &) { delete h; return -7; }
+  cudaMemset(h->scalars.p, 0, 16 * sizeof(int));
+  cudaMemset(h->counters.p, 0, 8 * sizeof(unsigned long long));
+  cudaMallocHost(&h->h_pinned, 64);
+  cudaEventCreate(&h->run_e0); cudaEventCreate(&h->run_e1);
+  h->ev.resize(2048);
+  for (auto &e : h->ev) cudaEventCreate(&e);
+  *out = h;
+  return 0;
+}
+
+int sh_destroy(sh_ctx *h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (auto &d : h->shape_dev) { d.Ap.release(); d.ab.release(); d.node.release(); }
+  h->d_shapes.release(); h->d_pk.release(); h->d_pm.release();
+  DevBuf<double> *db[] = {&h->x, &h->v, &h->q, &h->L, &h->f, &h->tq, &h->c, &h->Rs, &h->c0, &h->wallf, &h->ewall, &h->ke, &h->bbox, &h->slot, &h->pres};
+  for (auto *b : db) b->release();
+  DevBuf<int> *ib[] = {&h->shape, &h->cell_of, &h->cell_count, &h->cell_start, &h->cell_fill, &h->cell_atoms, &h->tile_sum, &h->cnt_full,
+                       &h->cnt_half, &h->nbr_off, &h->half_off, &h->nbr_j, &h->pair_i, &h->pair_j, &h->pair_eij, &h->pair_eji, &h->scalars};
+  for (auto *b : ib) b->release();
+  h->counters.release();
+  for (auto &e : h->ev) cudaEventDestroy(e);
+  if (h->h_pinned) cudaFreeHost(h->h_pinned);
+  h->stage.release();
+  cudaEventDestroy(h->run_e0); cudaEventDestroy(h->run_e1);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+const char *sh_last_error(const sh_ctx *h) { return h ? h->err.c_str() : "null handle"; }
+
+int sh_set_box(sh_ctx *h, const double lo[3], const double hi[3], const int periodic[3]) {
+  for (int d = 0; d < 3; d++) if (!(hi[d] > lo[d])) return fail(h, "box: hi <= lo");
+  for (int d = 0; d < 3; d++) { h->lo[d] = lo[d]; h->hi[d] = hi[d]; h->periodic[d] = periodic[d] != 0; }
+  h->box_set = true; h->forces_valid = false; h->list_valid = false;
+  return 0;
+}
+
+int sh_set_quadrature(sh_ctx *h, int n_theta, int n_phi) {
+  if (!h->shapes.empty()) return fail(h, "set_quadrature must precede add_shape");
+  if (n_theta < 2 || n_phi < 4) return fail(h, "quadrature too small");
+  if ((long)n_theta * n_phi > 65535) return fail(h, "quadrature has more than 65535 nodes");
+  h->n_theta = n_theta; h->n_phi = n_phi;
+  return 0;
+}
+
+int sh_add_shape(sh_ctx *h, int lmax, const double *a_lm, const double *b_lm, double density, int *shape_id_out) {
+  if ((int)h->shapes.size() >= SH_MAX_SHAPES) return fail(h, "too many shapes");
+  ShapeTables t;
+  std::string e = build_shape_tables(lmax, a_lm, b_lm, density, h->n_theta, h->n_phi, t);
+  if (!e.empty()) return fail(h, e);
+  h->shapes.push_back(std::move(t));
+  h->shapes_dirty = true; h->forces_valid = false; h->list_valid = false;
+  if (shape_id_out) *shape_id_out = (int)h->shapes.size() - 1;
+  return 0;
+}
+
+int sh_get_shape_props(const sh_ctx *h, int shape, double *volume, double com[3], double inertia[3],
+                       double quat_principal[4], double *rmax, double *rmin) {
+  if (shape < 0 || shape >= (int)h->shapes.size()) return -1;
+  const ShapeTables &s = h->shapes[shape];
+  if (volume) *volume = s.volume;
+  if (com) for (int d = 0; d < 3; d++) com[d] = s.com[d];
+  if (inertia) for (int d = 0; d < 3; d++) inertia[d] = s.inertia[d];
+  if (quat_principal) for (int d = 0; d < 4; d++) quat_principal[d] = s.quat_principal[d];
+  if (rmax) *rmax = s.rmax;
+  if (rmin) *rmin = s.rmin;
+  return 0;
+}
+
+int sh_get_nodes(const sh_ctx *h, int shape, double *p, double *nds) {
+  if (shape < 0 || shape >= (int)h->shapes.size()) return -1;
+  const ShapeTables &s = h->shapes[shape];
+  for (int k = 0; k < s.nq; k++)
+    for (int d = 0; d < 3; d++) { if (p) p[3 * k + d] = s.node_p[d][k]; if (nds) nds[3 * k + d] = s.node_n[d][k]; }
+  return 0;
+}
+
+int sh_set_atoms(sh_ctx *h, int64_t n, const int64_t *tag, const int *shape, const double *x, const double *v,
+                 const double *quat, const double *angmom) {
+  if (n < 0 || n > (int64_t)1 << 30) return fail(h, "bad atom count");
+  if (n > 0 && (!shape || !x)) return fail(h, "shape and x are required");
+  const int ns = (int)h->shapes.size();
+  for (int64_t i = 0; i < n; i++) if (shape[i] < 0 || shape[i] >= ns) return fail(h, "atom shape id out of range");
+  CU(cudaSetDevice(h->device));
+  const int st = (int)((n + 31) / 32 * 32) + 32;
+  try {
+    h->x.ensure(3 * (size_t)st); h->v.ensure(3 * (size_t)st); h->q.ensure(4 * (size_t)st); h->L.ensure(3 * (size_t)st);
+    h->f.ensure(3 * (size_t)st); h->tq.ensure(3 * (size_t)st); h->c.ensure(3 * (size_t)st); h->Rs.ensure(9 * (size_t)st);
+    h->c0.ensure(3 * (size_t)st); h->wallf.ensure(6 * (size_t)st); h->ewall.ensure(st); h->ke.ensure(2 * (size_t)st);
+    h->shape.ensure(st);
+  } catch (std::string &e) { return fail(h, e); }
+  h->n = n; h->stride = st;
+  std::vector<double> buf((size_t)4 * st, 0.0);
+  auto up = [&](DevBuf<double> &dst, const double *src, int ncomp, bool is_quat) -> cudaError_t {
+    std::fill(buf.begin(), buf.end(), 0.0);
+    for (int64_t i = 0; i < n; i++) {
+      if (src) {
+        double nn = 1.0;
+        if (is_quat) {
+          nn = std::sqrt(src[4 * i] * src[4 * i] + src[4 * i + 1] * src[4 * i + 1] + src[4 * i + 2] * src[4 * i + 2] + src[4 * i + 3] * src[4 * i + 3]);
+        }
+        for (int d = 0; d < ncomp; d++) buf[(size_t)d * st + i] = is_quat ? src[ncomp * i + d] / nn : src[ncomp * i + d];
+      } else if (is_quat) buf[i] = 1.0;
+    }
+    return cudaMemcpy(dst.p, buf.data(), (size_t)ncomp * st * sizeof(double), cudaMemcpyHostToDevice);
+  };
+  if (quat) for (int64_t i = 0; i < n; i++) {
+    double nn = quat[4 * i] * quat[4 * i] + quat[4 * i + 1] * quat[4 * i + 1] + quat[4 * i + 2] * quat[4 * i + 2] + quat[4 * i + 3] * quat[4 * i + 3];
+    if (!(nn > 0)) return fail(h, "zero quaternion");
+  }
+  CU(up(h->x, x, 3, false)); CU(up(h->v, v, 3, false)); CU(up(h->q, quat, 4, true)); CU(up(h->L, angmom, 3, false));
+  CU(cudaMemset(h->f.p, 0, 3 * (size_t)st * 8)); CU(cudaMemset(h->tq.p, 0, 3 * (size_t)st * 8));
+  CU(cudaMemset(h->wallf.p, 0, 6 * (size_t)st * 8)); CU(cudaMemset(h->ewall.p, 0, (size_t)st * 8));
+  CU(cudaMemset(h->c0.p, 0, 3 * (size_t)st * 8));
+  std::vector<int> sh(st, 0);
+  for (int64_t i = 0; i < n; i++) sh[i] = shape[i];
+  CU(cudaMemcpy(h->shape.p, sh.data(), (size_t)st * sizeof(int), cudaMemcpyHostToDevice));
+  h->tag.resize(n);
+  for (int64_t i = 0; i < n; i++) h->tag[i] = tag ? tag[i] : i + 1;
+  h->forces_valid = false; h->list_valid = false; h->npairs = 0; h->nentries = 0;
+  return 0;
+}
+
+int sh_pair_coeff(sh_ctx *h, int si, int sj, double k, double exponent) {
+  if (si < 0 || sj < 0 || si >= SH_MAX_SHAPES || sj >= SH_MAX_SHAPES) return fail(h, "pair_coeff: shape out of range");
+  if (!(k >= 0) || !(exponent >= 1.0)) return fail(h, "pair_coeff: need k >= 0, exponent >= 1");
+  h->pk[si * SH_MAX_SHAPES + sj] = h->pk[sj * SH_MAX_SHAPES + si] = k;
+  h->pm[si * SH_MAX_SHAPES + sj] = h->pm[sj * SH_MAX_SHAPES + si] = exponent;
+  h->coeff_dirty = true; h->forces_valid = false;
+  return 0;
+}
+
+int sh_add_wall(sh_ctx *h, const double point[3], const double normal[3], double k, double exponent) {
+  if (h->walls.n >= 16) return fail(h, "too many walls");
+  const double nn = std::sqrt(normal[0] * normal[0] + normal[1] * normal[1] + normal[2] * normal[2]);
+  if (!(nn > 0)) return fail(h, "wall normal is zero");
+  if (!(k >= 0) || !(exponent >= 1.0)) return fail(h, "wall: need k >= 0, exponent >= 1");
+  const int w = h->walls.n++;
+  for (int d = 0; d < 3; d++) { h->walls.c[w][d] = point[d]; h->walls.nrm[w][d] = normal[d] / nn; }
+  h->walls.k[w] = k; h->walls.m[w] = exponent;
+  h->forces_valid = false;
+  return 0;
+}
+
+int sh_set_gravity(sh_ctx *h, const double g[3]) { for (int d = 0; d < 3; d++) h->g[d] = g[d]; return 0; }
+
+int sh_set_neighbor(sh_ctx *h, double skin, int every, int check) {
+  if (skin < 0) return fail(h, "skin < 0");
+  if (every < 1) return fail(h, "every < 1");
+  h->skin = skin; h->neigh_every = every; h->neigh_check = check != 0;
+  h->list_valid = false; h->forces_valid = false;
+  return 0;
+}
+
+int sh_set_timestep(sh_ctx *h, double dt) { if (!(dt > 0)) return fail(h, "dt <= 0"); h->dt = dt; return 0; }
+
+int sh_set_pair_tuning(sh_ctx *h, int threads_per_cta, int ctas_per_sm, int variant) {
+  if (threads_per_cta != 0 && threads_per_cta != 64 && threads_per_cta != 128 && threads_per_cta != 256)
+    return fail(h, "threads_per_cta must be 0, 64, 128 or 256");
+  h->tune_threads = threads_per_cta; h->tune_ctas_per_sm = ctas_per_sm; h->tune_variant = variant;
+  return 0;
+}
+
+int sh_compute_forces(sh_ctx *h) {
+  CU(cudaSetDevice(h->device));
+  int rc = setup_forces(h);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int sh_run(sh_ctx *h, int64_t nsteps) {
+  CU(cudaSetDevice(h->device));
+  int rc;
+  if (!h->forces_valid || !h->list_valid) { if ((rc = setup_forces(h))) return rc; }
+  const int n = (int)h->n;
+  if (n == 0) return 0;
+  const int nb = cdiv(n, 256);
+  const double trig = 0.5 * h->skin, trig2 = trig * trig;
+  int *d_flag = h->scalars.p + 1;
+  CU(cudaEventRecord(h->run_e0, h->stream));
+  for (int64_t step = 0; step < nsteps; step++) {
+    AtomView A = view(h);
+    integrate_initial_kernel<<<nb, 256, 0, h->stream>>>(A, h->d_shapes.p, h->dt, h->g[0], h->g[1], h->g[2], trig2, d_flag);
+    h->kernel_launches++;
+    h->steps_since_build++;
+    bool rebuild = false;
+    if (h->steps_since_build >= h->neigh_every) {
+      if (h->neigh_check) {
+        CU(cudaMemcpyAsync(h->h_pinned + 4, d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        rebuild = h->h_pinned[4] != 0;
+      } else rebuild = true;
+    }
+    if (rebuild) { if ((rc = build_neighbors(h))) return rc; }
+    if ((rc = compute_forces_device(h))) return rc;
+    integrate_final_kernel<<<nb, 256, 0, h->stream>>>(A, h->d_shapes.p, h->dt, h->g[0], h->g[1], h->g[2]);
+    h->kernel_launches++;
+  }
+  CU(cudaEventRecord(h->run_e1, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaGetLastError());
+  { float ms = 0; cudaEventElapsedTime(&ms, h->run_e0, h->run_e1); h->sec_run_last = ms * 1e-3; h->sec_run_total += h->sec_run_last; }
+  return 0;
+}
+
+int sh_get_run_time(const sh_ctx *h, double *seconds_last_run, double *seconds_total) {
+  if (seconds_last_run) *seconds_last_run = h->sec_run_last;
+  if (seconds_total) *seconds_total = h->sec_run_total;
+  return 0;
+}
+
+// Pair::compute-style offload: the caller owns the atoms, pushes x / quat (and optionally v, angmom)
+// every step, keeps the neighbor list alive across calls (rebuilt when the skin is exhausted).
+int sh_put_state(sh_ctx *h, int64_t n, const double *x, const double *v, const double *quat, const double *angmom) {
+  if (n != h->n) return fail(h, "put_state: n mismatch");
+  CU(cudaSetDevice(h->device));
+  if (n == 0) return 0;
+  const int st = h->stride, nb = cdiv(n, 256);
+  try { h->stage.ensure((size_t)4 * n); } catch (std::string &e) { return fail(h, e); }
+  struct Item { const double *src; double *dst; int nc; int norm; } items[4] = {
+      {x, h->x.p, 3, 0}, {v, h->v.p, 3, 0}, {quat, h->q.p, 4, 1}, {angmom, h->L.p, 3, 0}};
+  for (auto &it : items) {
+    if (!it.src) continue;
+    CU(cudaMemcpyAsync(h->stage.p, it.src, (size_t)it.nc * n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    aos_to_soa_kernel<<<nb, 256, 0, h->stream>>>(h->stage.p, it.dst, (int)n, it.nc, st, it.norm);
+    h->kernel_launches++;
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  h->forces_valid = false;
+  return 0;
+}
+
+int sh_get_forces(const sh_ctx *hc, int64_t n, double *f, double *torque) {
+  sh_ctx *h = const_cast<sh_ctx *>(hc);
+  if (n != h->n) return fail(h, "get_forces: n mismatch");
+  CU(cudaSetDevice(h->device));
+  if (n == 0) return 0;
+  const int st = h->stride, nb = cdiv(n, 256);
+  try { h->stage.ensure((size_t)6 * n); } catch (std::string &e) { return fail(h, e); }
+  soa_to_aos_kernel<<<nb, 256, 0, h->stream>>>(h->f.p, h->stage.p, (int)n, 3, st);
+  soa_to_aos_kernel<<<nb, 256, 0, h->stream>>>(h->tq.p, h->stage.p + 3 * n, (int)n, 3, st);
+  h->kernel_launches += 2;
+  if (f) CU(cudaMemcpyAsync(f, h->stage.p, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (torque) CU(cudaMemcpyAsync(torque, h->stage.p + 3 * n, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int sh_get_natoms(const sh_ctx *h, int64_t *n) { if (n) *n = h->n; return 0; }
+
+int sh_get_atoms(const sh_ctx *hc, int64_t n, double *x, double *v, double *quat, double *angmom, double *f, double *torque) {
+  sh_ctx *h = const_cast<sh_ctx *>(hc);
+  if (n != h->n) return fail(h, "get_atoms: n mismatch");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  const int st = h->stride;
+  std::vector<double> buf((size_t)4 * st);
+  auto down = [&](const DevBuf<double> &src, double *dst, int ncomp) -> cudaError_t {
+    if (!dst) return cudaSuccess;
+    cudaError_t e = cudaMemcpy(buf.data(), src.p, (size_t)ncomp * st * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return e;
+    for (int64_t i = 0; i < n; i++) for (int d = 0; d < ncomp; d++) dst[ncomp * i + d] = buf[(size_t)d * st + i];
+    return cudaSuccess;
+  };
+  CU(down(h->x, x, 3)); CU(down(h->v, v, 3)); CU(down(h->q, quat, 4)); CU(down(h->L, angmom, 3));
+  CU(down(h->f, f, 3)); CU(down(h->tq, torque, 3));
+  return 0;
+}
+
+int sh_get_pairs(const sh_ctx *hc, int64_t cap, int64_t *npairs, int64_t *tag_i, int64_t *tag_j, double *V, double *F,
+                 double *tau_i, double *tau_j, double *centroid) {
+  sh_ctx *h = const_cast<sh_ctx *>(hc);
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  const int np = h->forces_valid ? h->npairs : 0;
+  if (npairs) *npairs = np;
+  const int m = (int)std::min<int64_t>(np, cap);
+  if (m <= 0) return 0;
+  std::vector<int> pi(m), pj(m);
+  CU(cudaMemcpy(pi.data(), h->pair_i.p, m * sizeof(int), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(pj.data(), h->pair_j.p, m * sizeof(int), cudaMemcpyDeviceToHost));
+  std::vector<double> buf((size_t)14 * m);
+  for (int r = 0; r < 14; r++)
+    CU(cudaMemcpy(buf.data() + (size_t)r * m, h->pres.p + (size_t)r * h->pres_stride, m * sizeof(double), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < m; k++) {
+    if (tag_i) tag_i[k] = h->tag[pi[k]];
+    if (tag_j) tag_j[k] = h->tag[pj[k]];
+    if (V) V[k] = buf[k];
+    for (int r = 0; r < 3; r++) {
+      if (F) F[3 * k + r] = buf[(size_t)(2 + r) * m + k];
+      if (tau_i) tau_i[3 * k + r] = buf[(size_t)(5 + r) * m + k];
+      if (tau_j) tau_j[3 * k + r] = buf[(size_t)(8 + r) * m + k];
+      if (centroid) centroid[3 * k + r] = buf[(size_t)(11 + r) * m + k];
+    }
+  }
+  return 0;
+}
+
+int sh_get_energy(const sh_ctx *hc, double *ke_trans, double *ke_rot, double *e_contact) {
+  sh_ctx *h = const_cast<sh_ctx *>(hc);
+  CU(cudaSetDevice(h->device));
+  const int n = (int)h->n;
+  double kt = 0, kr = 0, ec = 0;
+  if (n > 0) {
+    int rc = prepare(h);
+    if (rc) return rc;
+    energy_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(view(h), h->d_shapes.p, h->ke.p);
+    h->kernel_launches++;
+    CU(cudaStreamSynchronize(h->stream));
+    std::vector<double> buf(2 * (size_t)n);
+    CU(cudaMemcpy(buf.data(), h->ke.p, 2 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++) { kt += buf[i]; kr += buf[n + i]; }
+    if (h->forces_valid) {
+      if (h->npairs > 0) {
+        std::vector<double> e(h->npairs);
+        CU(cudaMemcpy(e.data(), h->pres.p + (size_t)h->pres_stride, h->npairs * sizeof(double), cudaMemcpyDeviceToHost));
+        for (double vv : e) ec += vv;
+      }
+      if (h->walls.n > 0) {
+        std::vector<double> e(n);
+        CU(cudaMemcpy(e.data(), h->ewall.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+        for (double vv : e) ec += vv;
+      }
+    }
+  }
+  if (ke_trans) *ke_trans = kt;
+  if (ke_rot) *ke_rot = kr;
+  if (e_contact) *e_contact = ec;
+  return 0;
+}
+
+int sh_get_counters(const sh_ctx *hc, int64_t *pair_evals, int64_t *nodes_transformed, int64_t *nodes_evaluated,
+                    int64_t *nodes_inside, int64_t *neighbor_builds, int64_t *kernel_launches) {
+  sh_ctx *h = const_cast<sh_ctx *>(hc);
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  unsigned long long c[4];
+  CU(cudaMemcpy(c, h->counters.p, sizeof c, cudaMemcpyDeviceToHost));
+  if (pair_evals) *pair_evals = (int64_t)c[0];
+  if (nodes_transformed) *nodes_transformed = (int64_t)c[1];
+  if (nodes_evaluated) *nodes_evaluated = (int64_t)c[2];
+  if (nodes_inside) *nodes_inside = (int64_t)c[3];
+  if (neighbor_builds) *neighbor_builds = h->neighbor_builds;
+  if (kernel_launches) *kernel_launches = h->kernel_launches;
+  return 0;
+}
+
+int sh_get_timers(const sh_ctx *hc, double *seconds_pair, int64_t *pair_launches, double *seconds_neigh, double *seconds_other) {
+  sh_ctx *h = const_cast<sh_ctx *>(hc);
+  CU(cudaSetDevice(h->device));
+  int rc = drain_events(h);
+  if (rc) return rc;
+  if (seconds_pair) *seconds_pair = h->sec_pair;
+  if (pair_launches) *pair_launches = h->pair_launches;
+  if (seconds_neigh) *seconds_neigh = h->sec_neigh;
+  if (seconds_other) *seconds_other = h->sec_other;
+  return 0;
+}
+
+int sh_reset_timers(sh_ctx *h) {
+  CU(cudaSetDevice(h->device));
+  int rc = drain_events(h);
+  if (rc) return rc;
+  h->sec_pair = h->sec_neigh = h->sec_other = 0; h->pair_launches = 0; h->sec_run_total = 0;
+  h->neighbor_builds = 0; h->kernel_launches = 0;
+  CU(cudaMemset(h->counters.p, 0, 8 * sizeof(unsigned long long)));
+  return 0;
+}
+
+int sh_measure_fp64_peak(sh_ctx *h, double *flops_per_s, double *sm_clock_mhz_est) {
+  CU(cudaSetDevice(h->device));
+  const int threads = 256, blocks = h->sm_count * 8, iters = 4096;
+  DevBuf<double> out;
+  try { out.ensure((size_t)threads * blocks); } catch (std::string &e) { return fail(h, e); }
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  double best = 0;
+  for (int rep = 0; rep < 5; rep++) {
+    CU(cudaEventRecord(e0, h->stream));
+    dfma_peak_kernel<<<blocks, threads, 0, h->stream>>>(out.p, iters, 1.0000001, 1e-9);
+    CU(cudaEventRecord(e1, h->stream));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double fl = 2.0 * 64.0 * iters * (double)threads * blocks / (ms * 1e-3);
+    if (rep > 0) best = std::max(best, fl);
+  }
+  h->kernel_launches += 5;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  out.release();
+  if (flops_per_s) *flops_per_s = best;
+  if (sm_clock_mhz_est) *sm_clock_mhz_est = best / (2.0 * 64.0 * h->sm_count) * 1e-6;  // if 64 FP64 lanes/SM
+  CU(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

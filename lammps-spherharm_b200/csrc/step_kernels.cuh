@@ -1,0 +1,293 @@
+// step_kernels.cuh — per-step kernels around the pair kernel:
+// pose, integrator (fix nve/sh-style), plane-wall contact (A.6), per-atom gather.
+// Reference sources (fix nve/sh, wall fix, atom style): NOT IN MOUNT.
+#pragma once
+#include "device_math.cuh"
+
+namespace shgpu {
+
+struct AtomView {
+  double *x, *v, *q, *L, *f, *tq;  // SoA [comp*stride + i]
+  double *c, *Rs, *c0;             // SH origin, shape->space rotation, origin at last neighbor build
+  double *wallf;                   // 6 x stride: wall force / torque
+  int *shape;
+  int n, stride;
+};
+
+// Rs = R(q) Rp^T ; c = x - Rs com   
+__device__ __forceinline__ void pose_of(const DevShape &s, const double q[4], const double xx[3], double Rs[9],
+                                        double c[3]) {
+  double Rq[9];
+  quat_to_mat(q, Rq);
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      double m = Rq[3 * r] * s.Rp[3 * k];
+      m = fma(Rq[3 * r + 1], s.Rp[3 * k + 1], m);
+      m = fma(Rq[3 * r + 2], s.Rp[3 * k + 2], m);
+      Rs[3 * r + k] = m;
+    }
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    double t = Rs[3 * r] * s.com[0];
+    t = fma(Rs[3 * r + 1], s.com[1], t);
+    t = fma(Rs[3 * r + 2], s.com[2], t);
+    c[r] = xx[r] - t;
+  }
+}
+
+// pose of every atom; also raises the neighbor-rebuild flag when an SH origin has moved more than
+// sqrt(trigger2) since the last build (trigger2 < 0 disables the check)
+__global__ void pose_kernel(AtomView A, const DevShape *shapes, double trigger2, int *rebuild_flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n) return;
+  const int st = A.stride;
+  const DevShape &s = shapes[A.shape[i]];
+  double q[4] = {A.q[i], A.q[st + i], A.q[2 * st + i], A.q[3 * st + i]};
+  double xx[3] = {A.x[i], A.x[st + i], A.x[2 * st + i]};
+  double Rs[9], c[3];
+  pose_of(s, q, xx, Rs, c);
+#pragma unroll
+  for (int e = 0; e < 9; e++) A.Rs[e * st + i] = Rs[e];
+  double disp2 = 0;
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    A.c[d * st + i] = c[d];
+    const double dd = c[d] - A.c0[d * st + i];
+    disp2 += dd * dd;
+  }
+  if (trigger2 >= 0 && disp2 > trigger2) *rebuild_flag = 1;
+}
+
+// AoS (n x ncomp, host layout) <-> SoA (ncomp x stride, device layout) transposes for the C-ABI
+__global__ void aos_to_soa_kernel(const double *aos, double *soa, int n, int ncomp, int stride, int normalise) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double nn = 1.0;
+  if (normalise) {
+    double s2 = 0;
+    for (int d = 0; d < ncomp; d++) s2 += aos[(size_t)ncomp * i + d] * aos[(size_t)ncomp * i + d];
+    nn = sqrt(s2);
+  }
+  for (int d = 0; d < ncomp; d++) soa[(size_t)d * stride + i] = normalise ? aos[(size_t)ncomp * i + d] / nn : aos[(size_t)ncomp * i + d];
+}
+__global__ void soa_to_aos_kernel(const double *soa, double *aos, int n, int ncomp, int stride) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int d = 0; d < ncomp; d++) aos[(size_t)ncomp * i + d] = soa[(size_t)d * stride + i];
+}
+
+__device__ __forceinline__ void omega_from_angmom(const double q[4], const double L[3], const double I[3],
+                                                  double w[3]) {
+  double R[9];
+  quat_to_mat(q, R);
+  double wb[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const double lb = R[k] * L[0] + R[3 + k] * L[1] + R[6 + k] * L[2];
+    wb[k] = (I[k] > 0) ? lb / I[k] : 0.0;
+  }
+#pragma unroll
+  for (int r = 0; r < 3; r++) w[r] = R[3 * r] * wb[0] + R[3 * r + 1] * wb[1] + R[3 * r + 2] * wb[2];
+}
+__device__ __forceinline__ void vecquat(const double w[3], const double q[4], double o[4]) {
+  o[0] = -w[0] * q[1] - w[1] * q[2] - w[2] * q[3];
+  o[1] = q[0] * w[0] + w[1] * q[3] - w[2] * q[2];
+  o[2] = q[0] * w[1] + w[2] * q[1] - w[0] * q[3];
+  o[3] = q[0] * w[2] + w[0] * q[2] - w[1] * q[1];
+}
+__device__ __forceinline__ void qnormalize(double q[4]) {
+  const double n = 1.0 / sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+#pragma unroll
+  for (int k = 0; k < 4; k++) q[k] *= n;
+}
+
+// first half of velocity-Verlet + Richardson quaternion step + pose + displacement flag
+__global__ void integrate_initial_kernel(AtomView A, const DevShape *shapes, double dt, double g0, double g1,
+                                         double g2, double trigger2, int *rebuild_flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n) return;
+  const int st = A.stride;
+  const DevShape &s = shapes[A.shape[i]];
+  const double dth = 0.5 * dt, im = 1.0 / s.mass;
+  const double g[3] = {g0, g1, g2};
+  double xx[3], L[3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    double v = A.v[d * st + i];
+    v += dth * (A.f[d * st + i] * im + g[d]);
+    A.v[d * st + i] = v;
+    xx[d] = A.x[d * st + i] + dt * v;
+    A.x[d * st + i] = xx[d];
+    L[d] = A.L[d * st + i] + dth * A.tq[d * st + i];
+    A.L[d * st + i] = L[d];
+  }
+  double q[4] = {A.q[i], A.q[st + i], A.q[2 * st + i], A.q[3 * st + i]};
+  {
+    const double dtq = dth;
+    double w[3], wq[4], qf[4], qh[4];
+    omega_from_angmom(q, L, s.inertia, w);
+    vecquat(w, q, wq);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { qf[k] = q[k] + dtq * wq[k]; qh[k] = q[k] + 0.5 * dtq * wq[k]; }
+    qnormalize(qf); qnormalize(qh);
+    omega_from_angmom(qh, L, s.inertia, w);
+    vecquat(w, qh, wq);
+#pragma unroll
+    for (int k = 0; k < 4; k++) qh[k] += 0.5 * dtq * wq[k];
+    qnormalize(qh);
+#pragma unroll
+    for (int k = 0; k < 4; k++) q[k] = 2.0 * qh[k] - qf[k];
+    qnormalize(q);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) A.q[k * st + i] = q[k];
+  double Rs[9], c[3];
+  pose_of(s, q, xx, Rs, c);
+#pragma unroll
+  for (int e = 0; e < 9; e++) A.Rs[e * st + i] = Rs[e];
+  double disp2 = 0;
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    A.c[d * st + i] = c[d];
+    const double dd = c[d] - A.c0[d * st + i];
+    disp2 += dd * dd;
+  }
+  if (disp2 > trigger2) *rebuild_flag = 1;
+}
+
+__global__ void integrate_final_kernel(AtomView A, const DevShape *shapes, double dt, double g0, double g1,
+                                       double g2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n) return;
+  const int st = A.stride;
+  const DevShape &s = shapes[A.shape[i]];
+  const double dth = 0.5 * dt, im = 1.0 / s.mass;
+  const double g[3] = {g0, g1, g2};
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    A.v[d * st + i] += dth * (A.f[d * st + i] * im + g[d]);
+    A.L[d * st + i] += dth * A.tq[d * st + i];
+  }
+}
+
+// ---- plane walls: one warp per atom, all walls in sequence -------------------------
+struct WallSet {
+  int n;
+  double c[16][3], nrm[16][3], k[16], m[16];
+};
+
+__global__ void wall_kernel(AtomView A, const DevShape *shapes, WallSet W, double *e_wall /* per atom */) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= A.n) return;
+  const int i = gw, st = A.stride;
+  const DevShape &s = shapes[A.shape[i]];
+  double f[3] = {0, 0, 0}, tq[3] = {0, 0, 0}, esum = 0;
+  for (int w = 0; w < W.n; w++) {
+    const double dc0 = A.c[i] - W.c[w][0], dc1 = A.c[st + i] - W.c[w][1], dc2 = A.c[2 * st + i] - W.c[w][2];
+    const double h = fma(dc2, W.nrm[w][2], fma(dc1, W.nrm[w][1], dc0 * W.nrm[w][0]));
+    if (h >= s.rmax) continue;
+    double R[9], nb[3];
+#pragma unroll
+    for (int e = 0; e < 9; e++) R[e] = A.Rs[e * st + i];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      double t = R[r] * W.nrm[w][0];
+      t = fma(R[3 + r], W.nrm[w][1], t);
+      t = fma(R[6 + r], W.nrm[w][2], t);
+      nb[r] = t;
+    }
+    const double x0[3] = {-h * nb[0], -h * nb[1], -h * nb[2]};
+    double S0 = 0, S1 = 0, S2 = 0, Av = 0, T0 = 0, T1 = 0, T2 = 0;
+    int cnt = 0;
+    for (int k = lane; k < s.nq; k += 32) {
+      const double p0 = s.px[k], p1 = s.py[k], p2 = s.pz[k];
+      const double gg = fma(nb[2], p2, fma(nb[1], p1, fma(nb[0], p0, h)));
+      if (gg < 0) {
+        const double n0 = s.nx[k], n1 = s.ny[k], n2 = s.nz[k];
+        const double dp0 = p0 - x0[0], dp1 = p1 - x0[1], dp2 = p2 - x0[2];
+        Av += fma(dp2, n2, fma(dp1, n1, dp0 * n0));
+        S0 += n0; S1 += n1; S2 += n2;
+        T0 += fma(p1, n2, -(p2 * n1));
+        T1 += fma(p2, n0, -(p0 * n2));
+        T2 += fma(p0, n1, -(p1 * n0));
+        cnt++;
+      }
+    }
+    S0 = warp_sum(S0); S1 = warp_sum(S1); S2 = warp_sum(S2); Av = warp_sum(Av);
+    T0 = warp_sum(T0); T1 = warp_sum(T1); T2 = warp_sum(T2);
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    const double V = Av / 3.0;
+    if (cnt == 0 || !(V > 0)) continue;
+    double E, pr;
+    if (W.m[w] == 1.0) { E = W.k[w] * V; pr = W.k[w]; }
+    else { const double pw = pow(V, W.m[w] - 1.0); E = W.k[w] * pw * V; pr = W.m[w] * W.k[w] * pw; }
+    esum += E;
+    double Ss[3], Ts[3], l[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      Ss[r] = R[3 * r] * S0 + R[3 * r + 1] * S1 + R[3 * r + 2] * S2;
+      Ts[r] = R[3 * r] * T0 + R[3 * r + 1] * T1 + R[3 * r + 2] * T2;
+      l[r] = A.c[r * st + i] - A.x[r * st + i];
+    }
+    const double Tt[3] = {Ts[0] + (l[1] * Ss[2] - l[2] * Ss[1]), Ts[1] + (l[2] * Ss[0] - l[0] * Ss[2]),
+                          Ts[2] + (l[0] * Ss[1] - l[1] * Ss[0])};
+#pragma unroll
+    for (int r = 0; r < 3; r++) { f[r] += -pr * Ss[r]; tq[r] += -pr * Tt[r]; }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int r = 0; r < 3; r++) { A.wallf[r * st + i] = f[r]; A.wallf[(3 + r) * st + i] = tq[r]; }
+    e_wall[i] = esum;
+  }
+}
+
+// ---- deterministic per-atom accumulation: fixed-order sum of the entry slots ----
+__global__ void gather_kernel(AtomView A, const int *nbr_off, const double *slot, int slot_stride, int use_wall) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n) return;
+  const int st = A.stride;
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  const int e0 = nbr_off[i], e1 = nbr_off[i + 1];
+  for (int e = e0; e < e1; e++) {
+#pragma unroll
+    for (int r = 0; r < 6; r++) acc[r] += slot[(size_t)r * slot_stride + e];
+  }
+  if (use_wall) {
+#pragma unroll
+    for (int r = 0; r < 6; r++) acc[r] += A.wallf[r * st + i];
+  }
+#pragma unroll
+  for (int r = 0; r < 3; r++) { A.f[r * st + i] = acc[r]; A.tq[r * st + i] = acc[3 + r]; }
+}
+
+// ---- energies (thermo) --------------------------------------------------------------------------
+__global__ void energy_kernel(AtomView A, const DevShape *shapes, double *ke /* 2 x n */) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n) return;
+  const int st = A.stride;
+  const DevShape &s = shapes[A.shape[i]];
+  const double v0 = A.v[i], v1 = A.v[st + i], v2 = A.v[2 * st + i];
+  ke[i] = 0.5 * s.mass * (v0 * v0 + v1 * v1 + v2 * v2);
+  double q[4] = {A.q[i], A.q[st + i], A.q[2 * st + i], A.q[3 * st + i]};
+  double L[3] = {A.L[i], A.L[st + i], A.L[2 * st + i]}, w[3];
+  omega_from_angmom(q, L, s.inertia, w);
+  ke[A.n + i] = 0.5 * (w[0] * L[0] + w[1] * L[1] + w[2] * L[2]);
+}
+
+// ---- K0: FP64 FMA-pipe peak -----------------------------------------------------------------------
+__global__ void dfma_peak_kernel(double *out, int iters, double a, double b) {
+  double r0 = threadIdx.x * 1e-3, r1 = r0 + 1, r2 = r0 + 2, r3 = r0 + 3, r4 = r0 + 4, r5 = r0 + 5, r6 = r0 + 6,
+         r7 = r0 + 7;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      r0 = fma(r0, a, b); r1 = fma(r1, a, b); r2 = fma(r2, a, b); r3 = fma(r3, a, b);
+      r4 = fma(r4, a, b); r5 = fma(r5, a, b); r6 = fma(r6, a, b); r7 = fma(r7, a, b);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+}
+
+}  // namespace shgpu

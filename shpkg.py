@@ -1,0 +1,21 @@
+"""Import helper: the package directory is `lammps-spherharm_b200/` (hyphenated, as the build
+contract names it), which Python cannot import by name.  `load()` registers it in sys.modules
+as `lammps_spherharm_b200`."""
+import importlib.util
+import os
+import sys
+
+NAME = "lammps_spherharm_b200"
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG_DIR = os.path.join(ROOT, "lammps-spherharm_b200")
+
+
+def load():
+    if NAME in sys.modules:
+        return sys.modules[NAME]
+    spec = importlib.util.spec_from_file_location(NAME, os.path.join(PKG_DIR, "__init__.py"),
+                                                  submodule_search_locations=[PKG_DIR])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[NAME] = mod
+    spec.loader.exec_module(mod)
+    return mod
