@@ -22,7 +22,7 @@ def pair_rel_errors(pg, po, rscale=1.0):
     assert np.array_equal(Vg > 0, Vo > 0), "contact / no-contact decision differs"
     m = Vo > 0
     if not m.any():
-        return dict(V=0.0, F=0.0, tau=0.0, ncontact=0)
+        return dict(V=0.0, F=0.0, tau=0.0, centroid=0.0, ncontact=0)
     eV = np.max(np.abs(Vg[m] - Vo[m]) / Vo[m])
     Fg, Fo = pg["F"][ig][m], po["F"][io][m]
     fn = np.linalg.norm(Fo, axis=1)
