@@ -20,6 +20,10 @@ struct DevShape {
   const double2 *ab;                      // folded (a,b) coefficients, m-major
   const double *px, *py, *pz;             // node points, shape frame
   const double *nx, *ny, *nz;             // oriented area elements n dS, shape frame
+  int n_theta, n_phi;                     // node k = row*n_phi + col; phi_col = (col+1/2) 2pi/n_phi
+  int tab_off;                            // offset (in terms) of this shape in the concatenated table
+  int pad_;
+  const float *row_x;                     // cos(theta_row), float copy for the conservative window
 };
 
 // rotation matrix (row-major R[3*r+c]) of unit quaternion (w,x,y,z); plain mul/add, fixed order

@@ -212,6 +212,7 @@ std::string build_shape_tables(int lmax, const double *a_lm, const double *b_lm,
   for (int d = 0; d < 3; d++) { s.node_p[d].assign(nq, 0.0); s.node_n[d].assign(nq, 0.0); }
   std::vector<double> gx, gw, P;
   gauss_legendre_nodes(nt, gx, gw);
+  s.row_x = gx;
   const double dphi = 2.0 * kPi / np;
   double vol = 0, m1[3] = {0, 0, 0}, Io[3][3] = {{0}};
   double rmax = 0, rmin = 1e300;

@@ -21,6 +21,7 @@ struct ShapeTables {
   std::vector<double> ah, bh;            // coefficients with alpha_lm * c_m folded in
   // node table, SoA: px,py,pz, nx,ny,nz (oriented area elements n dS)
   std::vector<double> node_p[3], node_n[3];
+  std::vector<double> row_x;             // cos(theta) of the Gauss-Legendre rows (node k = row*n_phi+col)
   double density = 1, volume = 0, mass = 0;
   std::array<double, 3> com{}, inertia{};
   std::array<double, 4> quat_principal{};

@@ -16,6 +16,7 @@
 #include "../../include/shgpu.h"
 #include "neighbor_kernels.cuh"
 #include "pair_kernel.cuh"
+#include "pair_warp_kernel.cuh"
 #include "shape_tables.h"
 #include "step_kernels.cuh"
 
@@ -40,6 +41,7 @@ struct DevBuf {
 struct ShapeDev {
   DevBuf<double> Ap, node;   // node: 6 x nq
   DevBuf<double2> ab;
+  DevBuf<float> row_x;
 };
 
 }  // namespace
@@ -59,6 +61,7 @@ struct sh_ctx {
   std::vector<DevShape> shape_host_view;
   DevBuf<DevShape> d_shapes;
   bool shapes_dirty = true;
+  int total_terms = 0;
   std::vector<double> pk, pm;  // SH_MAX_SHAPES^2
   DevBuf<double> d_pk, d_pm;
   bool coeff_dirty = true;
@@ -121,7 +124,11 @@ int upload_shapes(sh_ctx *h) {
       const ShapeTables &t = h->shapes[s];
       ShapeDev &d = h->shape_dev[s];
       if (d.Ap.p) continue;  // already uploaded
-      d.Ap.ensure(t.nterms); d.ab.ensure(t.nterms); d.node.ensure((size_t)6 * t.nq);
+      d.Ap.ensure(t.nterms); d.ab.ensure(t.nterms); d.node.ensure((size_t)6 * t.nq); d.row_x.ensure(t.n_theta);
+      {
+        std::vector<float> rx(t.row_x.begin(), t.row_x.end());
+        CU(cudaMemcpy(d.row_x.p, rx.data(), rx.size() * sizeof(float), cudaMemcpyHostToDevice));
+      }
       std::vector<double2> ab(t.nterms);
       for (int k = 0; k < t.nterms; k++) ab[k] = make_double2(t.ah[k], t.bh[k]);
       CU(cudaMemcpy(d.Ap.p, t.Ap.data(), t.nterms * sizeof(double), cudaMemcpyHostToDevice));
@@ -139,7 +146,11 @@ int upload_shapes(sh_ctx *h) {
       v.Ap = d.Ap.p; v.ab = d.ab.p;
       v.px = d.node.p; v.py = d.node.p + t.nq; v.pz = d.node.p + 2 * (size_t)t.nq;
       v.nx = d.node.p + 3 * (size_t)t.nq; v.ny = d.node.p + 4 * (size_t)t.nq; v.nz = d.node.p + 5 * (size_t)t.nq;
+      v.n_theta = t.n_theta; v.n_phi = t.n_phi; v.pad_ = 0; v.row_x = d.row_x.p;
     }
+    int off = 0;
+    for (int s = 0; s < ns; s++) { h->shape_host_view[s].tab_off = off; off += h->shapes[s].nterms; }
+    h->total_terms = off;
     h->d_shapes.ensure(std::max(ns, 1));
   } catch (std::string &e) { return fail(h, e); }
   if (ns) CU(cudaMemcpy(h->d_shapes.p, h->shape_host_view.data(), ns * sizeof(DevShape), cudaMemcpyHostToDevice));
@@ -293,6 +304,19 @@ int launch_pair(sh_ctx *h, const PairArgs &A, int ctas_per_sm, size_t smem) {
   return 0;
 }
 
+template <int NW, bool SMEM_TABLES>
+int launch_pair_warp(sh_ctx *h, const PairArgs &A, int ctas_per_sm) {
+  const size_t smem = pair_warp_smem_bytes(h->total_terms, NW, SMEM_TABLES);
+  CU(cudaFuncSetAttribute(pair_warp_kernel<NW, SMEM_TABLES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+  int occ = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pair_warp_kernel<NW, SMEM_TABLES>, NW * 32, smem));
+  if (occ < 1) return fail(h, "pair warp kernel does not fit on an SM");
+  if (ctas_per_sm > 0) occ = std::min(occ, ctas_per_sm);
+  const int grid = std::max(1, std::min((A.npairs + NW - 1) / NW, occ * h->sm_count));
+  pair_warp_kernel<NW, SMEM_TABLES><<<grid, NW * 32, smem, h->stream>>>(A, (int)h->shapes.size(), h->total_terms);
+  return 0;
+}
+
 int compute_forces_device(sh_ctx *h) {
   const int n = (int)h->n;
   if (n == 0) { h->forces_valid = true; return 0; }
@@ -310,13 +334,27 @@ int compute_forces_device(sh_ctx *h) {
     for (auto &s : h->shapes) { maxT = std::max(maxT, s.nterms); maxq = std::max(maxq, s.nq); }
     P.max_terms = maxT; P.max_nq = maxq;
     CU(cudaMemsetAsync(h->scalars.p + 2, 0, sizeof(int), h->stream));
-    int nt = h->tune_threads ? h->tune_threads : 128;
+    const int nt = h->tune_threads ? h->tune_threads : 128;
     if (h->ev_used + 2 > h->ev.size()) { if (drain_events(h)) return -2; }
     CU(cudaEventRecord(h->ev[h->ev_used], h->stream));
     int rc;
-    if (nt == 256) rc = launch_pair<256>(h, P, h->tune_ctas_per_sm, pair_smem_bytes(maxT, maxq, 8));
-    else if (nt == 64) rc = launch_pair<64>(h, P, h->tune_ctas_per_sm, pair_smem_bytes(maxT, maxq, 2));
-    else rc = launch_pair<128>(h, P, h->tune_ctas_per_sm, pair_smem_bytes(maxT, maxq, 4));
+    if (h->tune_variant == 1) {          // CTA-per-pair kernel (full-table scan)
+      if (nt == 256) rc = launch_pair<256>(h, P, h->tune_ctas_per_sm, pair_smem_bytes(maxT, maxq, 8));
+      else if (nt == 64) rc = launch_pair<64>(h, P, h->tune_ctas_per_sm, pair_smem_bytes(maxT, maxq, 2));
+      else rc = launch_pair<128>(h, P, h->tune_ctas_per_sm, pair_smem_bytes(maxT, maxq, 4));
+    } else {                             // warp-per-pair kernel (default)
+      const bool fits = pair_warp_smem_bytes(h->total_terms, 16, true) <= 200 * 1024;
+      const int tw = h->tune_threads ? h->tune_threads : 512;
+      if (fits) {
+        if (tw == 256) rc = launch_pair_warp<8, true>(h, P, h->tune_ctas_per_sm);
+        else if (tw == 128) rc = launch_pair_warp<4, true>(h, P, h->tune_ctas_per_sm);
+        else if (tw == 384) rc = launch_pair_warp<12, true>(h, P, h->tune_ctas_per_sm);
+        else rc = launch_pair_warp<16, true>(h, P, h->tune_ctas_per_sm);
+      } else {
+        if (tw == 256) rc = launch_pair_warp<8, false>(h, P, h->tune_ctas_per_sm);
+        else rc = launch_pair_warp<16, false>(h, P, h->tune_ctas_per_sm);
+      }
+    }
     if (rc) return rc;
     CU(cudaEventRecord(h->ev[h->ev_used + 1], h->stream));
     h->ev_used += 2;
@@ -398,7 +436,7 @@ int sh_destroy(sh_ctx *h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  for (auto &d : h->shape_dev) { d.Ap.release(); d.ab.release(); d.node.release(); }
+  for (auto &d : h->shape_dev) { d.Ap.release(); d.ab.release(); d.node.release(); d.row_x.release(); }
   h->d_shapes.release(); h->d_pk.release(); h->d_pm.release();
   DevBuf<double> *db[] = {&h->x, &h->v, &h->q, &h->L, &h->f, &h->tq, &h->c, &h->Rs, &h->c0, &h->wallf, &h->ewall, &h->ke, &h->bbox, &h->slot, &h->pres};
   for (auto *b : db) b->release();
@@ -544,8 +582,8 @@ int sh_set_neighbor(sh_ctx *h, double skin, int every, int check) {
 int sh_set_timestep(sh_ctx *h, double dt) { if (!(dt > 0)) return fail(h, "dt <= 0"); h->dt = dt; return 0; }
 
 int sh_set_pair_tuning(sh_ctx *h, int threads_per_cta, int ctas_per_sm, int variant) {
-  if (threads_per_cta != 0 && threads_per_cta != 64 && threads_per_cta != 128 && threads_per_cta != 256)
-    return fail(h, "threads_per_cta must be 0, 64, 128 or 256");
+  if (threads_per_cta != 0 && threads_per_cta != 64 && threads_per_cta != 128 && threads_per_cta != 256 && threads_per_cta != 384 && threads_per_cta != 512)
+    return fail(h, "threads_per_cta must be 0, 64, 128, 256 or 512");
   h->tune_threads = threads_per_cta; h->tune_ctas_per_sm = ctas_per_sm; h->tune_variant = variant;
   return 0;
 }
