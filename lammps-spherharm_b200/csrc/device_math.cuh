@@ -21,8 +21,8 @@ struct DevShape {
   const double *px, *py, *pz;             // node points, shape frame
   const double *nx, *ny, *nz;             // oriented area elements n dS, shape frame
   int n_theta, n_phi;                     // node k = row*n_phi + col; phi_col = (col+1/2) 2pi/n_phi
-  int tab_off;                            // offset (in terms) of this shape in the concatenated table
-  int pad_;
+  int tab_off;                            // offset (in records) of this shape in the concatenated table
+  int nterms4;                            // nterms rounded up to a multiple of 4; tables hold nterms4+4 records
   const float *row_x;                     // cos(theta_row), float copy for the conservative window
 };
 
@@ -75,6 +75,99 @@ __device__ __forceinline__ double sh_radius_folded(int L, const double *__restri
   }
   rho_out = rho;
   return r;
+}
+
+// Software-pipelined form of sh_radius_folded for tables padded to a multiple of 4 records plus 4
+// (zero records): the coefficient records of the NEXT four terms are fetched while the current
+// four are consumed, so the shared-memory latency is off the dependent chain.  Every term runs the
+// same body; a block (fixed m) starts from the state q1 = 0, q2 = -1, C = S = 0, which makes the
+// generic body reproduce the special first two terms exactly:
+//   l = m   : tx = 0*x,  q = fma(tx, 0, 1) = 1,        C = fma(a, 1, 0) = a
+//   l = m+1 : q = fma(Ap*x, 1, -0) = Ap*x (the rounded product), as in sh_radius_folded.
+// Bit-identical to sh_radius_folded (and to the oracle) up to the sign of a zero accumulator.
+__device__ __forceinline__ double sh_radius_folded_pipe(int L, int nterms4, const double *__restrict__ Ap,
+                                                        const double2 *__restrict__ ab, double s0, double s1,
+                                                        double s2, double rho2, double &rho_out) {
+  const double rho = sqrt(rho2);
+  const double inv = 1.0 / rho;
+  const double x = s2 * inv, zx = s0 * inv, zy = s1 * inv;
+  double u = 1.0, v = 0.0, r = 0.0, C = 0.0, S = 0.0, q1 = 0.0, q2 = -1.0;
+  int m = 0, bend = L;
+  double nA0 = Ap[0], nA1 = Ap[1], nA2 = Ap[2], nA3 = Ap[3];
+  double2 nC0 = ab[0], nC1 = ab[1], nC2 = ab[2], nC3 = ab[3];
+#pragma unroll 1
+  for (int idx = 0; idx < nterms4; idx += 4) {
+    const double cA0 = nA0, cA1 = nA1, cA2 = nA2, cA3 = nA3;
+    const double2 cC0 = nC0, cC1 = nC1, cC2 = nC2, cC3 = nC3;
+    nA0 = Ap[idx + 4]; nA1 = Ap[idx + 5]; nA2 = Ap[idx + 6]; nA3 = Ap[idx + 7];
+    nC0 = ab[idx + 4]; nC1 = ab[idx + 5]; nC2 = ab[idx + 6]; nC3 = ab[idx + 7];
+#define SH_TERM(cA, cC, J)                                                      \
+    {                                                                           \
+      const double tx = (cA) * x;                                               \
+      const double q = fma(tx, q1, -q2);                                        \
+      C = fma((cC).x, q, C); S = fma((cC).y, q, S);                             \
+      q2 = q1; q1 = q;                                                          \
+      if (idx + (J) == bend) {                                                  \
+        r = fma(u, C, r); r = fma(v, S, r);                                     \
+        m++; bend += L + 1 - m;                                                 \
+        const double t1 = v * zy, un = fma(u, zx, -t1);                         \
+        const double t2 = v * zx, vn = fma(u, zy, t2);                          \
+        u = un; v = vn; C = 0.0; S = 0.0; q1 = 0.0; q2 = -1.0;                  \
+      }                                                                         \
+    }
+    SH_TERM(cA0, cC0, 0) SH_TERM(cA1, cC1, 1) SH_TERM(cA2, cC2, 2) SH_TERM(cA3, cC3, 3)
+#undef SH_TERM
+  }
+  rho_out = rho;
+  return r;
+}
+
+// Two points per thread against the SAME shape: the coefficient loads (1 LDS.64 + 1 LDS.128 per
+// term) are shared by both points and the two recurrences are independent dependency chains.
+// Measured on B200 (tools/dfma_probe.cu): 67-73 % FP64-pipe utilisation against 57-61 % for the
+// one-point loop at 16-32 warps/SM.  Per point the operation sequence is exactly that of
+// sh_radius_folded, so each result is bit-identical to the one-point evaluation.
+__device__ __forceinline__ void sh_radius_folded_x2(int L, const double *__restrict__ Ap,
+                                                    const double2 *__restrict__ ab, const double sA[3],
+                                                    double rhoA2, const double sB[3], double rhoB2, double &rhoA,
+                                                    double &rhoB, double &rA_out, double &rB_out) {
+  const double rA = sqrt(rhoA2), iA = 1.0 / rA, rB = sqrt(rhoB2), iB = 1.0 / rB;
+  const double xA = sA[2] * iA, zxA = sA[0] * iA, zyA = sA[1] * iA;
+  const double xB = sB[2] * iB, zxB = sB[0] * iB, zyB = sB[1] * iB;
+  double uA = 1.0, vA = 0.0, rrA = 0.0, uB = 1.0, vB = 0.0, rrB = 0.0;
+  int base = 0;
+  for (int m = 0; m <= L; m++) {
+    if (m > 0) {
+      const double a1 = vA * zyA, un = fma(uA, zxA, -a1), a2 = vA * zxA, vn = fma(uA, zyA, a2);
+      uA = un; vA = vn;
+      const double b1 = vB * zyB, wn = fma(uB, zxB, -b1), b2 = vB * zxB, yn = fma(uB, zyB, b2);
+      uB = wn; vB = yn;
+    }
+    const double2 c0 = ab[base];
+    double CA = c0.x, SA = c0.y, CB = c0.x, SB = c0.y;
+    const int len = L - m;
+    if (len >= 1) {
+      const double ap1 = Ap[base + 1];
+      double qA1 = ap1 * xA, qA2 = 1.0, qB1 = ap1 * xB, qB2 = 1.0;
+      const double2 c1 = ab[base + 1];
+      CA = fma(c1.x, qA1, CA); SA = fma(c1.y, qA1, SA);
+      CB = fma(c1.x, qB1, CB); SB = fma(c1.y, qB1, SB);
+#pragma unroll 4
+      for (int i = 2; i <= len; i++) {
+        const double ap = Ap[base + i];
+        const double2 ci = ab[base + i];
+        const double txA = ap * xA, txB = ap * xB;
+        const double qA = fma(txA, qA1, -qA2), qB = fma(txB, qB1, -qB2);
+        CA = fma(ci.x, qA, CA); CB = fma(ci.x, qB, CB);
+        SA = fma(ci.y, qA, SA); SB = fma(ci.y, qB, SB);
+        qA2 = qA1; qA1 = qA; qB2 = qB1; qB1 = qB;
+      }
+    }
+    rrA = fma(uA, CA, rrA); rrA = fma(vA, SA, rrA);
+    rrB = fma(uB, CB, rrB); rrB = fma(vB, SB, rrB);
+    base += len + 1;
+  }
+  rhoA = rA; rhoB = rB; rA_out = rrA; rB_out = rrB;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

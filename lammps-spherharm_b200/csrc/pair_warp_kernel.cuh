@@ -10,9 +10,10 @@
 //     nodes whose exact test would fail, so the exact FP64 test below still decides every node and
 //     the result is identical to a full scan (the parity tests check the evaluated/inside counters
 //     against the oracle's full scan, bit for bit);
-//   * STREAMING COMPACTION: survivors of the exact bounding-sphere test go to a 64-entry per-warp
-//     ring; whenever >= 32 are queued a full warp evaluates r_b with the folded recurrences
-//     (1 DMUL + 3 DFMA per (l,m) term) — every lane busy except in the last flush of a direction;
+//   * STREAMING COMPACTION: survivors of the exact bounding-sphere test go to a 128-entry per-warp
+//     ring; whenever >= 64 are queued the warp evaluates r_b for two points per lane with the folded
+//     recurrences (1 DMUL + 3 DFMA per (l,m) term and point; the two points share every coefficient
+//     load and form independent dependency chains) — every lane busy except in the last flush;
 //   * inside nodes are accumulated at once; the visiting order is a pure function of the pair, so the
 //     floating-point sums are bitwise reproducible run to run (no floating-point atomics).
 #pragma once
@@ -31,18 +32,20 @@ __global__ void __launch_bounds__(NW * 32) pair_warp_kernel(PairArgs A, int nsha
   double2 *s_ab = reinterpret_cast<double2 *>(smem_raw);
   double *s_Ap = reinterpret_cast<double *>(s_ab + (SMEM_TABLES ? total_terms : 0));
   double *s_dir = s_Ap + (SMEM_TABLES ? total_terms : 0);            // [NW][10] direction-0 sums
-  unsigned short *s_ring = reinterpret_cast<unsigned short *>(s_dir + NW * 10);  // [NW][64]
+  double *s_pose = s_dir + NW * 10;                                  // [NW][16] M[9], t[3], x0[3]
+  unsigned short *s_ring = reinterpret_cast<unsigned short *>(s_pose + NW * 16);  // [NW][128]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (SMEM_TABLES) {
     for (int s = 0; s < nshapes; s++) {
       const DevShape &sh = A.shapes[s];
-      for (int t = tid; t < sh.nterms; t += NW * 32) { s_ab[sh.tab_off + t] = sh.ab[t]; s_Ap[sh.tab_off + t] = sh.Ap[t]; }
+      for (int t = tid; t < sh.nterms4 + 4; t += NW * 32) { s_ab[sh.tab_off + t] = sh.ab[t]; s_Ap[sh.tab_off + t] = sh.Ap[t]; }
     }
     __syncthreads();
   }
-  unsigned short *ring = s_ring + warp * 64;
+  unsigned short *ring = s_ring + warp * 128;
   double *dir0 = s_dir + warp * 10;
+  double *pose = s_pose + warp * 16;
   unsigned long long n_eval = 0, n_inside = 0, n_trans = 0, n_pairs = 0;
   const int st = A.stride;
 
@@ -69,36 +72,46 @@ __global__ void __launch_bounds__(NW * 32) pair_warp_kernel(PairArgs A, int nsha
       const DevShape &sb = A.shapes[dir ? shp_i : shp_j];
       const double sgn = dir ? -1.0 : 1.0;
       const double dd0 = sgn * d[0], dd1 = sgn * d[1], dd2 = sgn * d[2];
-      // relative pose, identical fma chains in every lane (uniform)
-      double M[9], t[3], x0[3];
-#pragma unroll
-      for (int r = 0; r < 3; r++) {
-        const double b0 = A.Rs[(0 + r) * st + b], b1 = A.Rs[(3 + r) * st + b], b2 = A.Rs[(6 + r) * st + b];
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          double m = b0 * A.Rs[(0 + k) * st + a];
-          m = fma(b1, A.Rs[(3 + k) * st + a], m);
-          m = fma(b2, A.Rs[(6 + k) * st + a], m);
-          M[3 * r + k] = m;
+      // relative pose: lanes 0..14 each produce one element (same fma chains as the oracle) into
+      // this warp's shared scratch; kept there (not in registers) to leave room for the eval pipeline
+      __syncwarp();
+      if (lane < 15) {
+        double val;
+        if (lane < 9) {
+          const int r = lane / 3, k = lane - 3 * r;
+          double m = A.Rs[(0 + r) * st + b] * A.Rs[(0 + k) * st + a];
+          m = fma(A.Rs[(3 + r) * st + b], A.Rs[(3 + k) * st + a], m);
+          m = fma(A.Rs[(6 + r) * st + b], A.Rs[(6 + k) * st + a], m);
+          val = m;
+        } else if (lane < 12) {
+          const int r = lane - 9;
+          double tt = A.Rs[(0 + r) * st + b] * dd0;
+          tt = fma(A.Rs[(3 + r) * st + b], dd1, tt);
+          tt = fma(A.Rs[(6 + r) * st + b], dd2, tt);
+          val = tt;
+        } else {
+          const int r = lane - 12;
+          double hx = A.Rs[(0 + r) * st + a] * dd0;
+          hx = fma(A.Rs[(3 + r) * st + a], dd1, hx);
+          hx = fma(A.Rs[(6 + r) * st + a], dd2, hx);
+          val = -0.5 * hx;
         }
-        double tt = b0 * dd0; tt = fma(b1, dd1, tt); tt = fma(b2, dd2, tt); t[r] = tt;
-        double hx = A.Rs[(0 + r) * st + a] * dd0;
-        hx = fma(A.Rs[(3 + r) * st + a], dd1, hx);
-        hx = fma(A.Rs[(6 + r) * st + a], dd2, hx);
-        x0[r] = -0.5 * hx;
+        pose[lane] = val;
       }
+      __syncwarp();
+      const double *M = pose, *t = pose + 9, *x0 = pose + 12;
       acc.S0 = acc.S1 = acc.S2 = acc.A = acc.T0 = acc.T1 = acc.T2 = acc.G0 = acc.G1 = acc.G2 = 0.0;
       acc.cnt = 0;
       const double rmax2 = sb.rmax2, rmin2 = sb.rmin2;
-      const double *__restrict__ px = sa.px, *__restrict__ py = sa.py, *__restrict__ pz = sa.pz;
-      const double *__restrict__ nx = sa.nx, *__restrict__ ny = sa.ny, *__restrict__ nz = sa.nz;
+      const double *__restrict__ nodes = sa.px;   // SoA block: px,py,pz,nx,ny,nz each nq long
+      const int nq = sa.nq;
       const double *tabAp = SMEM_TABLES ? (s_Ap + sb.tab_off) : sb.Ap;
       const double2 *tabab = SMEM_TABLES ? (s_ab + sb.tab_off) : sb.ab;
-      const int L = sb.lmax;
+      const int L = sb.lmax, nterms4 = sb.nterms4;
       int queued = 0;  // ring holds entries [0, queued)
 
       auto accumulate = [&](int k, double p0, double p1, double p2) {
-        const double n0 = nx[k], n1 = ny[k], n2 = nz[k];
+        const double n0 = nodes[3 * nq + k], n1 = nodes[4 * nq + k], n2 = nodes[5 * nq + k];
         const double dp0 = p0 - x0[0], dp1 = p1 - x0[1], dp2 = p2 - x0[2];
         const double dn = fma(dp2, n2, fma(dp1, n1, dp0 * n0));
         acc.S0 += n0; acc.S1 += n1; acc.S2 += n2;
@@ -112,7 +125,7 @@ __global__ void __launch_bounds__(NW * 32) pair_warp_kernel(PairArgs A, int nsha
       auto evaluate = [&](int count) {  // evaluate ring[0..count) with lanes < count
         if (lane < count) {
           const int k = ring[lane];
-          const double p0 = px[k], p1 = py[k], p2 = pz[k];
+          const double p0 = nodes[k], p1 = nodes[nq + k], p2 = nodes[2 * nq + k];
           double s0 = fma(M[0], p0, t[0]); s0 = fma(M[1], p1, s0); s0 = fma(M[2], p2, s0);
           double s1 = fma(M[3], p0, t[1]); s1 = fma(M[4], p1, s1); s1 = fma(M[5], p2, s1);
           double s2 = fma(M[6], p0, t[2]); s2 = fma(M[7], p1, s2); s2 = fma(M[8], p2, s2);
@@ -121,6 +134,33 @@ __global__ void __launch_bounds__(NW * 32) pair_warp_kernel(PairArgs A, int nsha
           const double r = sh_radius_folded(L, tabAp, tabab, s0, s1, s2, rho2, rho);
           if (rho < r) accumulate(k, p0, p1, p2);
         }
+      };
+      // two points per lane: ring[lane] and ring[32+lane]; slot B is valid for lane < count-32
+      auto evaluate2 = [&](int count) {
+        const int kA = ring[lane];
+        const bool validB = lane < count - 32;
+        const int kB = validB ? ring[32 + lane] : kA;
+        double sA[3], sB[3];
+        {
+          const double p0 = nodes[kA], p1 = nodes[nq + kA], p2 = nodes[2 * nq + kA];
+          double s0 = fma(M[0], p0, t[0]); s0 = fma(M[1], p1, s0); s0 = fma(M[2], p2, s0);
+          double s1 = fma(M[3], p0, t[1]); s1 = fma(M[4], p1, s1); s1 = fma(M[5], p2, s1);
+          double s2 = fma(M[6], p0, t[2]); s2 = fma(M[7], p1, s2); s2 = fma(M[8], p2, s2);
+          sA[0] = s0; sA[1] = s1; sA[2] = s2;
+        }
+        {
+          const double p0 = nodes[kB], p1 = nodes[nq + kB], p2 = nodes[2 * nq + kB];
+          double s0 = fma(M[0], p0, t[0]); s0 = fma(M[1], p1, s0); s0 = fma(M[2], p2, s0);
+          double s1 = fma(M[3], p0, t[1]); s1 = fma(M[4], p1, s1); s1 = fma(M[5], p2, s1);
+          double s2 = fma(M[6], p0, t[2]); s2 = fma(M[7], p1, s2); s2 = fma(M[8], p2, s2);
+          sB[0] = s0; sB[1] = s1; sB[2] = s2;
+        }
+        const double rhoA2 = fma(sA[2], sA[2], fma(sA[1], sA[1], sA[0] * sA[0]));
+        const double rhoB2 = fma(sB[2], sB[2], fma(sB[1], sB[1], sB[0] * sB[0]));
+        double rhoA, rhoB, rA, rB;
+        sh_radius_folded_x2(L, tabAp, tabab, sA, rhoA2, sB, rhoB2, rhoA, rhoB, rA, rB);
+        if (rhoA < rA) accumulate(kA, nodes[kA], nodes[nq + kA], nodes[2 * nq + kA]);
+        if (validB && rhoB < rB) accumulate(kB, nodes[kB], nodes[nq + kB], nodes[2 * nq + kB]);
       };
 
       // ---- conservative window on a's node grid (FP32 with margins; see header comment)
@@ -183,7 +223,7 @@ __global__ void __launch_bounds__(NW * 32) pair_warp_kernel(PairArgs A, int nsha
                 int col = rc0 + cc;
                 if (col >= nph) col -= nph;
                 k = rowbase + col;
-                const double p0 = px[k], p1 = py[k], p2 = pz[k];
+                const double p0 = nodes[k], p1 = nodes[nq + k], p2 = nodes[2 * nq + k];
                 double s0 = fma(M[0], p0, t[0]); s0 = fma(M[1], p1, s0); s0 = fma(M[2], p2, s0);
                 double s1 = fma(M[3], p0, t[1]); s1 = fma(M[4], p1, s1); s1 = fma(M[5], p2, s1);
                 double s2 = fma(M[6], p0, t[2]); s2 = fma(M[7], p1, s2); s2 = fma(M[8], p2, s2);
@@ -199,14 +239,14 @@ __global__ void __launch_bounds__(NW * 32) pair_warp_kernel(PairArgs A, int nsha
                 if (surv) ring[queued + __popc(sm & ((1u << lane) - 1u))] = (unsigned short)k;
                 queued += __popc(sm);
                 __syncwarp();
-                if (queued >= 32) {
-                  evaluate(32);
-                  n_eval += 32;
+                if (queued >= 64) {
+                  evaluate2(64);
+                  n_eval += 64;
                   __syncwarp();
-                  // move the remainder to the front
-                  const int rem = queued - 32;
+                  // move the remainder (< 32 entries) to the front
+                  const int rem = queued - 64;
                   unsigned short mv = 0;
-                  if (lane < rem) mv = ring[32 + lane];
+                  if (lane < rem) mv = ring[64 + lane];
                   __syncwarp();
                   if (lane < rem) ring[lane] = mv;
                   queued = rem;
@@ -216,7 +256,8 @@ __global__ void __launch_bounds__(NW * 32) pair_warp_kernel(PairArgs A, int nsha
             }
           }
         }
-        if (queued > 0) { evaluate(queued); n_eval += queued; __syncwarp(); }
+        if (queued > 32) { evaluate2(queued); n_eval += queued; __syncwarp(); }
+        else if (queued > 0) { evaluate(queued); n_eval += queued; __syncwarp(); }
       }
       // ---- warp reduction (fixed butterfly order)
       acc.S0 = warp_sum(acc.S0); acc.S1 = warp_sum(acc.S1); acc.S2 = warp_sum(acc.S2); acc.A = warp_sum(acc.A);
@@ -306,7 +347,7 @@ __global__ void __launch_bounds__(NW * 32) pair_warp_kernel(PairArgs A, int nsha
 inline size_t pair_warp_smem_bytes(int total_terms, int nw, bool smem_tables) {
   size_t b = 0;
   if (smem_tables) b += (size_t)total_terms * (sizeof(double2) + sizeof(double));
-  b += (size_t)nw * 10 * sizeof(double) + (size_t)nw * 64 * sizeof(unsigned short);
+  b += (size_t)nw * 26 * sizeof(double) + (size_t)nw * 128 * sizeof(unsigned short);
   return (b + 15) & ~(size_t)15;
 }
 

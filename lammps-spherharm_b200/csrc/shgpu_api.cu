@@ -124,7 +124,9 @@ int upload_shapes(sh_ctx *h) {
       const ShapeTables &t = h->shapes[s];
       ShapeDev &d = h->shape_dev[s];
       if (d.Ap.p) continue;  // already uploaded
-      d.Ap.ensure(t.nterms); d.ab.ensure(t.nterms); d.node.ensure((size_t)6 * t.nq); d.row_x.ensure(t.n_theta);
+      const int tpad = (t.nterms + 3) / 4 * 4 + 4;   // zero records pad the software-pipelined loop
+      d.Ap.ensure(tpad); d.ab.ensure(tpad); d.node.ensure((size_t)6 * t.nq); d.row_x.ensure(t.n_theta);
+      CU(cudaMemset(d.Ap.p, 0, tpad * sizeof(double))); CU(cudaMemset(d.ab.p, 0, tpad * sizeof(double2)));
       {
         std::vector<float> rx(t.row_x.begin(), t.row_x.end());
         CU(cudaMemcpy(d.row_x.p, rx.data(), rx.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -146,10 +148,10 @@ int upload_shapes(sh_ctx *h) {
       v.Ap = d.Ap.p; v.ab = d.ab.p;
       v.px = d.node.p; v.py = d.node.p + t.nq; v.pz = d.node.p + 2 * (size_t)t.nq;
       v.nx = d.node.p + 3 * (size_t)t.nq; v.ny = d.node.p + 4 * (size_t)t.nq; v.nz = d.node.p + 5 * (size_t)t.nq;
-      v.n_theta = t.n_theta; v.n_phi = t.n_phi; v.pad_ = 0; v.row_x = d.row_x.p;
+      v.n_theta = t.n_theta; v.n_phi = t.n_phi; v.nterms4 = (t.nterms + 3) / 4 * 4; v.row_x = d.row_x.p;
     }
     int off = 0;
-    for (int s = 0; s < ns; s++) { h->shape_host_view[s].tab_off = off; off += h->shapes[s].nterms; }
+    for (int s = 0; s < ns; s++) { h->shape_host_view[s].tab_off = off; off += h->shape_host_view[s].nterms4 + 4; }
     h->total_terms = off;
     h->d_shapes.ensure(std::max(ns, 1));
   } catch (std::string &e) { return fail(h, e); }
