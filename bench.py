@@ -94,6 +94,13 @@ def dist_env():
 def make_workload(args, pkg, n_particles=None):
     W = pkg.workloads
     n = n_particles or args.particles
+    if args.workload == "relaxed" and (args.lmax, args.ntheta, args.nphi) == (30, 48, 96):
+        # relaxed jammed unit cell (4000 particles) tiled periodically to ~n particles
+        t = max(1.0, n / 4000.0)
+        r = max(1, int(round(t ** (1.0 / 3.0))))
+        best = min(((abs(a * b * c - t), (a, b, c)) for a in (r - 1, r, r + 1) for b in (r - 1, r, r + 1)
+                    for c in (r - 1, r, r + 1) if a >= 1 and b >= 1 and c >= 1 and a >= b >= c), key=lambda u: u[0])[1]
+        return W.tiled_packing(best)
     return W.config3_packing(n, lmax=args.lmax, grid=(args.ntheta, args.nphi), seed=30)
 
 
@@ -153,10 +160,14 @@ def run_reference(args):
 
 
 def workload_config(args, n):
-    return {"workload": "BASELINE configs[2]: polydisperse-shape SH packing, 8 shape types, periodic FCC-seeded, "
-                        "packing fraction ~0.55", "n_particles": int(n), "lmax": args.lmax,
-            "quadrature": "%dx%d" % (args.ntheta, args.nphi), "l2_policy": "inputs+node tables re-streamed every step; "
-            "per-step pair/slot buffers (>= 100 MB at 100k) exceed nothing cached between steps is reused by design"}
+    kind = ("mechanically relaxed jammed packing (phi~0.71, compressed under damping by this code; 4000-particle "
+            "periodic unit cell tiled)") if args.workload == "relaxed" else "jittered FCC-seeded packing (phi~0.56)"
+    return {"workload": "BASELINE configs[2]: ~100k polydisperse-shape SH packing, 8 shape types, l_max=30, periodic; "
+                        + kind, "n_particles": int(n), "lmax": args.lmax,
+            "quadrature": "%dx%d" % (args.ntheta, args.nphi),
+            "l2_policy": "compute-bound FP64 kernel; the per-step working set (atom SoA + pair list + per-pair/per-entry "
+                         "result slots, ~150 MB at 100k particles) exceeds the 126 MB L2 and is rewritten every step; "
+                         "shape tables (1.8 MB) are L2/shared-memory resident by design"}
 
 
 def run_graft(args):
@@ -284,6 +295,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--particles", type=int, default=100000)
+    ap.add_argument("--workload", default="relaxed", choices=["relaxed", "lattice"],
+                    help="relaxed: committed jammed unit cell tiled periodically; lattice: jittered FCC sites")
     ap.add_argument("--lmax", type=int, default=30)
     ap.add_argument("--ntheta", type=int, default=48)
     ap.add_argument("--nphi", type=int, default=96)

@@ -56,6 +56,8 @@ int sh_set_gravity(sh_ctx *h, const double g[3]);
 int sh_set_neighbor(sh_ctx *h, double skin, int every, int check);
 /* timestep ------------------------------------------------------------------------------------- */
 int sh_set_timestep(sh_ctx *h, double dt);
+/* fix viscous-style damping: after each half kick v *= (1 - dt/2 gamma_lin), angmom *= (1 - dt/2 gamma_rot) */
+int sh_set_damping(sh_ctx *h, double gamma_lin, double gamma_rot);
 
 /* run N  (Verlet::setup + Verlet::run: fix nve/sh initial_integrate, neighbor decide/build,
  * Pair::compute, wall post_force, final_integrate) -------------------------------------------- */

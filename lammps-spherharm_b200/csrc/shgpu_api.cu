@@ -66,7 +66,7 @@ struct sh_ctx {
   DevBuf<double> d_pk, d_pm;
   bool coeff_dirty = true;
   WallSet walls{};
-  double g[3] = {0, 0, 0}, skin = 0.0, dt = 1e-4;
+  double g[3] = {0, 0, 0}, skin = 0.0, dt = 1e-4, gamma_lin = 0.0, gamma_rot = 0.0;
   int neigh_every = 1, neigh_check = 1;
   // atoms
   int64_t n = 0;
@@ -581,6 +581,12 @@ int sh_set_neighbor(sh_ctx *h, double skin, int every, int check) {
   return 0;
 }
 
+int sh_set_damping(sh_ctx *h, double gamma_lin, double gamma_rot) {
+  if (gamma_lin < 0 || gamma_rot < 0) return fail(h, "damping < 0");
+  h->gamma_lin = gamma_lin; h->gamma_rot = gamma_rot;
+  return 0;
+}
+
 int sh_set_timestep(sh_ctx *h, double dt) { if (!(dt > 0)) return fail(h, "dt <= 0"); h->dt = dt; return 0; }
 
 int sh_set_pair_tuning(sh_ctx *h, int threads_per_cta, int ctas_per_sm, int variant) {
@@ -608,10 +614,11 @@ int sh_run(sh_ctx *h, int64_t nsteps) {
   const int nb = cdiv(n, 256);
   const double trig = 0.5 * h->skin, trig2 = trig * trig;
   int *d_flag = h->scalars.p + 1;
+  const double damp_v = 1.0 - 0.5 * h->dt * h->gamma_lin, damp_L = 1.0 - 0.5 * h->dt * h->gamma_rot;
   CU(cudaEventRecord(h->run_e0, h->stream));
   for (int64_t step = 0; step < nsteps; step++) {
     AtomView A = view(h);
-    integrate_initial_kernel<<<nb, 256, 0, h->stream>>>(A, h->d_shapes.p, h->dt, h->g[0], h->g[1], h->g[2], trig2, d_flag);
+    integrate_initial_kernel<<<nb, 256, 0, h->stream>>>(A, h->d_shapes.p, h->dt, h->g[0], h->g[1], h->g[2], trig2, d_flag, damp_v, damp_L);
     h->kernel_launches++;
     h->steps_since_build++;
     bool rebuild = false;
@@ -624,7 +631,7 @@ int sh_run(sh_ctx *h, int64_t nsteps) {
     }
     if (rebuild) { if ((rc = build_neighbors(h))) return rc; }
     if ((rc = compute_forces_device(h))) return rc;
-    integrate_final_kernel<<<nb, 256, 0, h->stream>>>(A, h->d_shapes.p, h->dt, h->g[0], h->g[1], h->g[2]);
+    integrate_final_kernel<<<nb, 256, 0, h->stream>>>(A, h->d_shapes.p, h->dt, h->g[0], h->g[1], h->g[2], damp_v, damp_L);
     h->kernel_launches++;
   }
   CU(cudaEventRecord(h->run_e1, h->stream));

@@ -105,7 +105,7 @@ __device__ __forceinline__ void qnormalize(double q[4]) {
 
 // first half of velocity-Verlet + Richardson quaternion step + pose + displacement flag
 __global__ void integrate_initial_kernel(AtomView A, const DevShape *shapes, double dt, double g0, double g1,
-                                         double g2, double trigger2, int *rebuild_flag) {
+                                         double g2, double trigger2, int *rebuild_flag, double damp_v, double damp_L) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= A.n) return;
   const int st = A.stride;
@@ -117,10 +117,11 @@ __global__ void integrate_initial_kernel(AtomView A, const DevShape *shapes, dou
   for (int d = 0; d < 3; d++) {
     double v = A.v[d * st + i];
     v += dth * (A.f[d * st + i] * im + g[d]);
+    v *= damp_v;
     A.v[d * st + i] = v;
     xx[d] = A.x[d * st + i] + dt * v;
     A.x[d * st + i] = xx[d];
-    L[d] = A.L[d * st + i] + dth * A.tq[d * st + i];
+    L[d] = (A.L[d * st + i] + dth * A.tq[d * st + i]) * damp_L;
     A.L[d * st + i] = L[d];
   }
   double q[4] = {A.q[i], A.q[st + i], A.q[2 * st + i], A.q[3 * st + i]};
@@ -158,7 +159,7 @@ __global__ void integrate_initial_kernel(AtomView A, const DevShape *shapes, dou
 }
 
 __global__ void integrate_final_kernel(AtomView A, const DevShape *shapes, double dt, double g0, double g1,
-                                       double g2) {
+                                       double g2, double damp_v, double damp_L) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= A.n) return;
   const int st = A.stride;
@@ -167,8 +168,8 @@ __global__ void integrate_final_kernel(AtomView A, const DevShape *shapes, doubl
   const double g[3] = {g0, g1, g2};
 #pragma unroll
   for (int d = 0; d < 3; d++) {
-    A.v[d * st + i] += dth * (A.f[d * st + i] * im + g[d]);
-    A.L[d * st + i] += dth * A.tq[d * st + i];
+    A.v[d * st + i] = (A.v[d * st + i] + dth * (A.f[d * st + i] * im + g[d])) * damp_v;
+    A.L[d * st + i] = (A.L[d * st + i] + dth * A.tq[d * st + i]) * damp_L;
   }
 }
 

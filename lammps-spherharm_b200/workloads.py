@@ -177,6 +177,29 @@ def config3_packing(n_target=100000, lmax=30, grid=(48, 96), seed=30):
     return packing((m, m, m), lmax, grid, nshapes=8, seed=seed, name="cfg3_packing_%d_l%d" % (4 * m ** 3, lmax))
 
 
+def tiled_packing(reps=(3, 3, 3), snapshot=None, vel_sigma=0.02, seed=7, k=1e3, exponent=1.0, skin=0.05, dt=1e-4):
+    """Mechanically relaxed dense packing (tools/make_packing.py: compressed under damping with the GPU
+    code itself to the jamming density, phi ~ 0.71) replicated periodically reps = (rx, ry, rz) times.
+    The committed unit cell holds 4000 particles, 8 SH shape types, l_max = 30, 48x96 quadrature."""
+    import os
+    if snapshot is None:
+        snapshot = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "packing_l30_4000.npz")
+    z = np.load(snapshot, allow_pickle=False)
+    lmax, grid, nshapes, sseed = int(z["lmax"]), tuple(int(v) for v in z["grid"]), int(z["nshapes"]), int(z["seed"])
+    box = np.array(z["box"], dtype=float)
+    shapes = [perturbed_shape(lmax, sseed + s) for s in range(nshapes)]
+    shifts = np.array([[i, j, k2] for i in range(reps[0]) for j in range(reps[1]) for k2 in range(reps[2])], dtype=float)
+    x = (z["x"][None, :, :] + (shifts * box)[:, None, :]).reshape(-1, 3)
+    quat = np.tile(z["quat"], (len(shifts), 1))
+    sid = np.tile(z["shape_id"], len(shifts)).astype(np.int32)
+    n = len(x)
+    rng = np.random.default_rng(seed)
+    return dict(name="relaxed_packing_%d_l%d" % (n, lmax), lmax=lmax, grid=grid, shapes=shapes, density=1.0,
+                shape_id=sid, x=x, v=rng.normal(0, vel_sigma, size=(n, 3)), quat=quat, angmom=np.zeros((n, 3)),
+                box=(np.zeros(3), box * np.array(reps, dtype=float), (1, 1, 1)), coeff=(k, exponent), walls=[],
+                gravity=(0, 0, 0), skin=skin, dt=dt)
+
+
 def apply(sim, cfg):
     """Drive a sim object (sh_* call surface) with a config dict."""
     if cfg["box"] is not None:

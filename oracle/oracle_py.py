@@ -117,6 +117,9 @@ class Oracle:
     def set_neighbor(self, skin, every=1, check=1):
         self._ck(self.L.orc_set_neighbor(self.h, C.c_double(skin), int(every), int(check)))
 
+    def set_damping(self, gamma_lin, gamma_rot):
+        self._ck(self.L.orc_set_damping(self.h, C.c_double(gamma_lin), C.c_double(gamma_rot)))
+
     def set_timestep(self, dt):
         self._ck(self.L.orc_set_timestep(self.h, C.c_double(dt)))
 

@@ -49,7 +49,7 @@ struct orc_ctx {
   int nshape; shape_t shp[MAX_SHAPES];
   double pk[MAX_SHAPES][MAX_SHAPES], pm[MAX_SHAPES][MAX_SHAPES];
   int nwall; wall_t wall[MAX_WALLS];
-  double g[3], skin, dt; int nthreads;
+  double g[3], skin, dt, gamma_lin, gamma_rot; int nthreads;
   int64_t n; int64_t *tag; int *shape;
   double *x, *v, *q, *L, *f, *tq;   /* n*3, n*3, n*4, n*3, n*3, n*3 */
   double *Rs, *c;                   /* pose: n*9, n*3 */
@@ -394,6 +394,7 @@ int orc_add_wall(orc_ctx *c, const double point[3], const double normal[3], doub
 int orc_set_gravity(orc_ctx *c, const double g[3]) { for (int d = 0; d < 3; d++) c->g[d] = g[d]; return 0; }
 int orc_set_neighbor(orc_ctx *c, double skin, int every, int check) { (void)every; (void)check; if (skin < 0) return fail(c, "skin < 0"); c->skin = skin; return 0; }
 int orc_set_timestep(orc_ctx *c, double dt) { if (!(dt > 0)) return fail(c, "dt <= 0"); c->dt = dt; return 0; }
+int orc_set_damping(orc_ctx *c, double gl, double gr) { if (gl < 0 || gr < 0) return fail(c, "damping < 0"); c->gamma_lin = gl; c->gamma_rot = gr; return 0; }
 int orc_set_threads(orc_ctx *c, int nthreads) { c->nthreads = nthreads > 0 ? nthreads : 1; return 0; }
 
 /* ---------------- pose: Rs = R(q) Rp^T, c = x - Rs com ---------------- */
@@ -683,15 +684,16 @@ static void richardson(double q[4], const double L[3], const double I[3], double
 int orc_run(orc_ctx *c, int64_t nsteps) {
   if (!c->forces_valid) if (orc_compute_forces(c)) return -1;
   double dt = c->dt, dth = 0.5 * dt;
+  const double damp_v = 1.0 - 0.5 * dt * c->gamma_lin, damp_L = 1.0 - 0.5 * dt * c->gamma_rot;
   for (int64_t step = 0; step < nsteps; step++) {
 #pragma omp parallel for num_threads(c->nthreads)
     for (int64_t i = 0; i < c->n; i++) {
       const shape_t *s = &c->shp[c->shape[i]];
       double im = 1.0 / s->mass;
       for (int d = 0; d < 3; d++) {
-        c->v[3 * i + d] += dth * (c->f[3 * i + d] * im + c->g[d]);
+        c->v[3 * i + d] = (c->v[3 * i + d] + dth * (c->f[3 * i + d] * im + c->g[d])) * damp_v;
         c->x[3 * i + d] += dt * c->v[3 * i + d];
-        c->L[3 * i + d] += dth * c->tq[3 * i + d];
+        c->L[3 * i + d] = (c->L[3 * i + d] + dth * c->tq[3 * i + d]) * damp_L;
       }
       richardson(&c->q[4 * i], &c->L[3 * i], s->inertia, dth);
     }
@@ -701,8 +703,8 @@ int orc_run(orc_ctx *c, int64_t nsteps) {
       const shape_t *s = &c->shp[c->shape[i]];
       double im = 1.0 / s->mass;
       for (int d = 0; d < 3; d++) {
-        c->v[3 * i + d] += dth * (c->f[3 * i + d] * im + c->g[d]);
-        c->L[3 * i + d] += dth * c->tq[3 * i + d];
+        c->v[3 * i + d] = (c->v[3 * i + d] + dth * (c->f[3 * i + d] * im + c->g[d])) * damp_v;
+        c->L[3 * i + d] = (c->L[3 * i + d] + dth * c->tq[3 * i + d]) * damp_L;
       }
     }
   }

@@ -41,6 +41,7 @@ int orc_add_wall(orc_ctx *c, const double point[3], const double normal[3], doub
 int orc_set_gravity(orc_ctx *c, const double g[3]);
 int orc_set_neighbor(orc_ctx *c, double skin, int every, int check);
 int orc_set_timestep(orc_ctx *c, double dt);
+int orc_set_damping(orc_ctx *c, double gamma_lin, double gamma_rot);
 int orc_set_threads(orc_ctx *c, int nthreads);
 int orc_compute_forces(orc_ctx *c);
 int orc_run(orc_ctx *c, int64_t nsteps);
