@@ -65,6 +65,20 @@ int sh_run(sh_ctx *h, int64_t nsteps);
 /* one Pair::compute + wall post_force on the current state (run 0) ---------------------------- */
 int sh_compute_forces(sh_ctx *h);
 
+/* one timestep in two halves (the multi-rank driver exchanges ghosts in between) ---------------- */
+int sh_step_begin(sh_ctx *h, int *rebuild_wanted);   /* initial_integrate + neighbor decide (local)  */
+int sh_step_end(sh_ctx *h, int rebuild);             /* ghost poses, build, Pair::compute, final_integrate */
+int sh_synchronize(sh_ctx *h);
+int sh_mark_begin(sh_ctx *h);                        /* CUDA-event stopwatch on the library stream */
+int sh_mark_end(sh_ctx *h, double *seconds);
+
+/* multi-rank (Comm::borders / forward_comm of the atom style's pack_comm / unpack_comm): the last
+ * nghost atoms passed to sh_set_atoms are ghosts.  d_idx, d_shift, d_out, d_in are DEVICE pointers;
+ * a record is 7 doubles: x + shift (3), quat (4). ------------------------------------------------- */
+int sh_set_ghost_count(sh_ctx *h, int64_t nghost);
+int sh_pack_atoms(sh_ctx *h, int64_t m, const int *d_idx, const double *d_shift, double *d_out);
+int sh_unpack_ghosts(sh_ctx *h, int64_t first, int64_t m, const double *d_in);
+
 /* Pair::compute-style offload for a host code that owns the atoms (the drop-in a LAMMPS pair style
  * wrapper uses every step): push x / quat (v, angmom optional; NULL = keep), sh_compute_forces,
  * then read f / torque.  The neighbor list is kept across calls and rebuilt when the skin is

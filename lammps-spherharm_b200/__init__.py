@@ -6,3 +6,10 @@ fallback: constructing ShGpu without a CUDA device raises.
 """
 from .capi import ShGpu, ShGpuError, load_library, exported_symbols  # noqa: F401
 from . import workloads  # noqa: F401
+
+
+def load_decomp():
+    """Domain-decomposition driver (imports torch.distributed lazily)."""
+    import importlib
+    _d = importlib.import_module(__name__ + ".decomp")
+    return _d

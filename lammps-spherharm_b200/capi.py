@@ -163,6 +163,37 @@ class ShGpu:
             return C.cast(a, c_dp) if isinstance(a, int) else a.ctypes.data_as(c_dp)
         self._ck(self.L.sh_get_forces(self.h, C.c_int64(self.n), ptr(f), ptr(torque)))
 
+    # ---- multi-rank support (decomp.py drives these) ------------------------------------------
+    def set_ghost_count(self, nghost):
+        self._ck(self.L.sh_set_ghost_count(self.h, C.c_int64(nghost)))
+
+    def step_begin(self):
+        flag = C.c_int(0)
+        self._ck(self.L.sh_step_begin(self.h, C.byref(flag)))
+        return flag.value
+
+    def step_end(self, rebuild):
+        self._ck(self.L.sh_step_end(self.h, int(rebuild)))
+
+    def mark_begin(self):
+        self._ck(self.L.sh_mark_begin(self.h))
+
+    def mark_end(self):
+        s = C.c_double()
+        self._ck(self.L.sh_mark_end(self.h, C.byref(s)))
+        return s.value
+
+    def synchronize(self):
+        self._ck(self.L.sh_synchronize(self.h))
+
+    def pack_atoms(self, m, d_idx_ptr, d_shift_ptr, d_out_ptr):
+        """device pointers (ints): gathers x+shift, quat of atoms d_idx[0..m) into d_out (m x 7)."""
+        self._ck(self.L.sh_pack_atoms(self.h, C.c_int64(m), C.c_void_p(d_idx_ptr), C.c_void_p(d_shift_ptr),
+                                      C.c_void_p(d_out_ptr)))
+
+    def unpack_ghosts(self, first, m, d_in_ptr):
+        self._ck(self.L.sh_unpack_ghosts(self.h, C.c_int64(first), C.c_int64(m), C.c_void_p(d_in_ptr)))
+
     def get_run_time(self):
         a, b = C.c_double(), C.c_double()
         self._ck(self.L.sh_get_run_time(self.h, C.byref(a), C.byref(b)))

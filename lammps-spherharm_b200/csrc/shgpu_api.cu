@@ -69,7 +69,7 @@ struct sh_ctx {
   double g[3] = {0, 0, 0}, skin = 0.0, dt = 1e-4, gamma_lin = 0.0, gamma_rot = 0.0;
   int neigh_every = 1, neigh_check = 1;
   // atoms
-  int64_t n = 0;
+  int64_t n = 0, nghost = 0;   // n = owned + ghost atoms; the last nghost are ghosts (multi-rank)
   int stride = 0;
   DevBuf<double> x, v, q, L, f, tq, c, Rs, c0, wallf, ewall, ke;
   DevBuf<int> shape;
@@ -110,9 +110,10 @@ AtomView view(sh_ctx *h) {
   AtomView A;
   A.x = h->x.p; A.v = h->v.p; A.q = h->q.p; A.L = h->L.p; A.f = h->f.p; A.tq = h->tq.p;
   A.c = h->c.p; A.Rs = h->Rs.p; A.c0 = h->c0.p; A.wallf = h->wallf.p; A.shape = h->shape.p;
-  A.n = (int)h->n; A.stride = h->stride;
+  A.n = (int)(h->n - h->nghost); A.stride = h->stride;   // kernels over OWNED atoms
   return A;
 }
+AtomView view_all(sh_ctx *h) { AtomView A = view(h); A.n = (int)h->n; return A; }
 
 int upload_shapes(sh_ctx *h) {
   if (!h->shapes_dirty) return 0;
@@ -188,7 +189,7 @@ int exclusive_scan(sh_ctx *h, const int *in, int *out, int n, int *total_host) {
 }
 
 int build_neighbors(sh_ctx *h) {
-  const int n = (int)h->n, st = h->stride;
+  const int n = (int)h->n, st = h->stride, nown = (int)(h->n - h->nghost);
   cudaEvent_t e0, e1;
   CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
   CU(cudaEventRecord(e0, h->stream));
@@ -251,19 +252,20 @@ int build_neighbors(sh_ctx *h) {
   if (exclusive_scan(h, h->cell_count.p, h->cell_start.p, (int)ncell, nullptr)) return -1;
   bin_fill_kernel<<<nb, 256, 0, h->stream>>>(n, h->cell_of.p, h->cell_start.p, h->cell_fill.p, h->cell_atoms.p);
   bin_sort_kernel<<<cdiv(ncell, 256), 256, 0, h->stream>>>((int)ncell, h->cell_start.p, h->cell_atoms.p);
-  nbr_count_kernel<<<nb, 256, 0, h->stream>>>(h->c.p, h->shape.p, h->d_shapes.p, n, st, G, h->cell_of.p, h->cell_start.p,
+  const int nbo = std::max(1, cdiv(nown, 256));
+  nbr_count_kernel<<<nbo, 256, 0, h->stream>>>(h->c.p, h->shape.p, h->d_shapes.p, nown, st, G, h->cell_of.p, h->cell_start.p,
                                               h->cell_atoms.p, h->cnt_full.p, h->cnt_half.p);
   h->kernel_launches += 4;
   int nentries = 0, npairs = 0;
-  if (exclusive_scan(h, h->cnt_full.p, h->nbr_off.p, n, &nentries)) return -1;
-  if (exclusive_scan(h, h->cnt_half.p, h->half_off.p, n, &npairs)) return -1;
+  if (exclusive_scan(h, h->cnt_full.p, h->nbr_off.p, nown, &nentries)) return -1;
+  if (exclusive_scan(h, h->cnt_half.p, h->half_off.p, nown, &npairs)) return -1;
   try {
     h->nbr_j.ensure(nentries + 1); h->pair_i.ensure(npairs + 1); h->pair_j.ensure(npairs + 1);
     h->pair_eij.ensure(npairs + 1); h->pair_eji.ensure(npairs + 1);
     if ((size_t)nentries + 1 > (size_t)h->slot_stride) { h->slot_stride = (int)((nentries + 1) * 1.25) + 64; h->slot.release(); h->slot.ensure((size_t)6 * h->slot_stride); }
     if ((size_t)npairs + 1 > (size_t)h->pres_stride) { h->pres_stride = (int)((npairs + 1) * 1.25) + 64; h->pres.release(); h->pres.ensure((size_t)14 * h->pres_stride); }
   } catch (std::string &e) { return fail(h, e); }
-  nbr_fill_kernel<<<nb, 256, 0, h->stream>>>(h->c.p, h->shape.p, h->d_shapes.p, n, st, G, h->cell_of.p, h->cell_start.p,
+  nbr_fill_kernel<<<nbo, 256, 0, h->stream>>>(h->c.p, h->shape.p, h->d_shapes.p, nown, st, G, h->cell_of.p, h->cell_start.p,
                                              h->cell_atoms.p, h->nbr_off.p, h->half_off.p, h->nbr_j.p, h->pair_i.p,
                                              h->pair_j.p, h->pair_eij.p);
   pair_reverse_kernel<<<std::max(1, cdiv(npairs, 256)), 256, 0, h->stream>>>(npairs, h->pair_i.p, h->pair_j.p, h->nbr_off.p,
@@ -320,7 +322,7 @@ int launch_pair_warp(sh_ctx *h, const PairArgs &A, int ctas_per_sm) {
 }
 
 int compute_forces_device(sh_ctx *h) {
-  const int n = (int)h->n;
+  const int n = (int)(h->n - h->nghost);   // forces are accumulated on owned atoms only
   if (n == 0) { h->forces_valid = true; return 0; }
   AtomView A = view(h);
   const int nb = cdiv(n, 256);
@@ -386,7 +388,7 @@ int setup_forces(sh_ctx *h) {
   if ((rc = prepare(h))) return rc;
   if (h->n > 0) {
     const double trig = 0.5 * h->skin;
-    pose_kernel<<<cdiv(h->n, 256), 256, 0, h->stream>>>(view(h), h->d_shapes.p, h->list_valid ? trig * trig : -1.0, h->scalars.p + 1);
+    pose_kernel<<<cdiv(h->n, 256), 256, 0, h->stream>>>(view_all(h), h->d_shapes.p, h->list_valid ? trig * trig : -1.0, h->scalars.p + 1, 0, (int)h->n);
     h->kernel_launches++;
     bool rebuild = !h->list_valid;
     if (!rebuild) {
@@ -546,7 +548,7 @@ int sh_set_atoms(sh_ctx *h, int64_t n, const int64_t *tag, const int *shape, con
   CU(cudaMemcpy(h->shape.p, sh.data(), (size_t)st * sizeof(int), cudaMemcpyHostToDevice));
   h->tag.resize(n);
   for (int64_t i = 0; i < n; i++) h->tag[i] = tag ? tag[i] : i + 1;
-  h->forces_valid = false; h->list_valid = false; h->npairs = 0; h->nentries = 0;
+  h->forces_valid = false; h->list_valid = false; h->npairs = 0; h->nentries = 0; h->nghost = 0;
   return 0;
 }
 
@@ -605,39 +607,123 @@ int sh_compute_forces(sh_ctx *h) {
   return 0;
 }
 
+// ---- one timestep in two halves, so that a multi-rank driver can put the ghost exchange between them
+int sh_step_begin(sh_ctx *h, int *rebuild_wanted) {
+  CU(cudaSetDevice(h->device));
+  int rc;
+  if (!h->forces_valid || !h->list_valid) { if ((rc = setup_forces(h))) return rc; }
+  const int n = (int)(h->n - h->nghost);
+  if (rebuild_wanted) *rebuild_wanted = 0;
+  if (h->n == 0) return 0;
+  const double trig = 0.5 * h->skin, trig2 = trig * trig;
+  const double damp_v = 1.0 - 0.5 * h->dt * h->gamma_lin, damp_L = 1.0 - 0.5 * h->dt * h->gamma_rot;
+  int *d_flag = h->scalars.p + 1;
+  if (n > 0) {
+    integrate_initial_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(view(h), h->d_shapes.p, h->dt, h->g[0], h->g[1], h->g[2], trig2, d_flag, damp_v, damp_L);
+    h->kernel_launches++;
+  }
+  h->steps_since_build++;
+  bool rebuild = false;
+  if (h->steps_since_build >= h->neigh_every) {
+    if (h->neigh_check) {
+      CU(cudaMemcpyAsync(h->h_pinned + 4, d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+      rebuild = h->h_pinned[4] != 0;
+    } else rebuild = true;
+  }
+  if (rebuild_wanted) *rebuild_wanted = rebuild ? 1 : 0;
+  return 0;
+}
+
+int sh_step_end(sh_ctx *h, int rebuild) {
+  CU(cudaSetDevice(h->device));
+  int rc;
+  if (h->n == 0) return 0;
+  const int n = (int)(h->n - h->nghost);
+  const double damp_v = 1.0 - 0.5 * h->dt * h->gamma_lin, damp_L = 1.0 - 0.5 * h->dt * h->gamma_rot;
+  if (!h->list_valid) {  // atoms were re-set mid-step (migration): poses of all atoms
+    if ((rc = prepare(h))) return rc;
+    pose_kernel<<<cdiv(h->n, 256), 256, 0, h->stream>>>(view_all(h), h->d_shapes.p, -1.0, h->scalars.p + 1, 0, (int)h->n);
+    h->kernel_launches++;
+  } else if (h->nghost > 0) {   // ghost poses from the freshly received x / quat
+    pose_kernel<<<cdiv(h->nghost, 256), 256, 0, h->stream>>>(view_all(h), h->d_shapes.p, -1.0, h->scalars.p + 1, n, (int)h->nghost);
+    h->kernel_launches++;
+  }
+  if (rebuild || !h->list_valid) { if ((rc = build_neighbors(h))) return rc; }
+  if ((rc = compute_forces_device(h))) return rc;
+  if (n > 0) {
+    integrate_final_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(view(h), h->d_shapes.p, h->dt, h->g[0], h->g[1], h->g[2], damp_v, damp_L);
+    h->kernel_launches++;
+  }
+  return 0;
+}
+
 int sh_run(sh_ctx *h, int64_t nsteps) {
   CU(cudaSetDevice(h->device));
   int rc;
   if (!h->forces_valid || !h->list_valid) { if ((rc = setup_forces(h))) return rc; }
-  const int n = (int)h->n;
-  if (n == 0) return 0;
-  const int nb = cdiv(n, 256);
-  const double trig = 0.5 * h->skin, trig2 = trig * trig;
-  int *d_flag = h->scalars.p + 1;
-  const double damp_v = 1.0 - 0.5 * h->dt * h->gamma_lin, damp_L = 1.0 - 0.5 * h->dt * h->gamma_rot;
+  if (h->n == 0) return 0;
   CU(cudaEventRecord(h->run_e0, h->stream));
   for (int64_t step = 0; step < nsteps; step++) {
-    AtomView A = view(h);
-    integrate_initial_kernel<<<nb, 256, 0, h->stream>>>(A, h->d_shapes.p, h->dt, h->g[0], h->g[1], h->g[2], trig2, d_flag, damp_v, damp_L);
-    h->kernel_launches++;
-    h->steps_since_build++;
-    bool rebuild = false;
-    if (h->steps_since_build >= h->neigh_every) {
-      if (h->neigh_check) {
-        CU(cudaMemcpyAsync(h->h_pinned + 4, d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-        rebuild = h->h_pinned[4] != 0;
-      } else rebuild = true;
-    }
-    if (rebuild) { if ((rc = build_neighbors(h))) return rc; }
-    if ((rc = compute_forces_device(h))) return rc;
-    integrate_final_kernel<<<nb, 256, 0, h->stream>>>(A, h->d_shapes.p, h->dt, h->g[0], h->g[1], h->g[2], damp_v, damp_L);
-    h->kernel_launches++;
+    int rebuild = 0;
+    if ((rc = sh_step_begin(h, &rebuild))) return rc;
+    if ((rc = sh_step_end(h, rebuild))) return rc;
   }
   CU(cudaEventRecord(h->run_e1, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaGetLastError());
   { float ms = 0; cudaEventElapsedTime(&ms, h->run_e0, h->run_e1); h->sec_run_last = ms * 1e-3; h->sec_run_total += h->sec_run_last; }
+  return 0;
+}
+
+// ---- multi-rank support: the last nghost atoms of the arrays are ghosts (copies of atoms owned by
+// other ranks / periodic images): they take part in pairs with owned atoms but receive no force,
+// are not integrated and carry no neighbor-list rows.  Device-pointer pack / unpack for the per-step
+// forward exchange of ghost x and quat; the transport itself is NCCL
+// point-to-point issued by the host driver (lammps-spherharm_b200/decomp.py).
+int sh_set_ghost_count(sh_ctx *h, int64_t nghost) {
+  if (nghost < 0 || nghost > h->n) return fail(h, "ghost count out of range");
+  h->nghost = nghost; h->forces_valid = false; h->list_valid = false;
+  return 0;
+}
+int sh_pack_atoms(sh_ctx *h, int64_t m, const int *d_idx, const double *d_shift, double *d_out) {
+  CU(cudaSetDevice(h->device));
+  if (m > 0) {
+    pack_atoms_kernel<<<cdiv(m, 256), 256, 0, h->stream>>>(view_all(h), (int)m, d_idx, d_shift, d_out);
+    h->kernel_launches++;
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+int sh_unpack_ghosts(sh_ctx *h, int64_t first, int64_t m, const double *d_in) {
+  CU(cudaSetDevice(h->device));
+  if (first < 0 || first + m > h->n) return fail(h, "unpack range out of bounds");
+  if (m > 0) {
+    unpack_atoms_kernel<<<cdiv(m, 256), 256, 0, h->stream>>>(view_all(h), (int)first, (int)m, d_in);
+    h->kernel_launches++;
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+// CUDA-event stopwatch on the library's stream (for drivers that step through sh_step_begin/end)
+int sh_mark_begin(sh_ctx *h) {
+  CU(cudaSetDevice(h->device));
+  CU(cudaEventRecord(h->run_e0, h->stream));
+  return 0;
+}
+int sh_mark_end(sh_ctx *h, double *seconds) {
+  CU(cudaSetDevice(h->device));
+  CU(cudaEventRecord(h->run_e1, h->stream));
+  CU(cudaEventSynchronize(h->run_e1));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, h->run_e0, h->run_e1));
+  if (seconds) *seconds = ms * 1e-3;
+  return 0;
+}
+int sh_synchronize(sh_ctx *h) {
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaGetLastError());
   return 0;
 }
 
@@ -670,7 +756,7 @@ int sh_put_state(sh_ctx *h, int64_t n, const double *x, const double *v, const d
 
 int sh_get_forces(const sh_ctx *hc, int64_t n, double *f, double *torque) {
   sh_ctx *h = const_cast<sh_ctx *>(hc);
-  if (n != h->n) return fail(h, "get_forces: n mismatch");
+  if (n < 0 || n > h->n) return fail(h, "get_forces: n out of range");
   CU(cudaSetDevice(h->device));
   if (n == 0) return 0;
   const int st = h->stride, nb = cdiv(n, 256);
@@ -688,7 +774,7 @@ int sh_get_natoms(const sh_ctx *h, int64_t *n) { if (n) *n = h->n; return 0; }
 
 int sh_get_atoms(const sh_ctx *hc, int64_t n, double *x, double *v, double *quat, double *angmom, double *f, double *torque) {
   sh_ctx *h = const_cast<sh_ctx *>(hc);
-  if (n != h->n) return fail(h, "get_atoms: n mismatch");
+  if (n < 0 || n > h->n) return fail(h, "get_atoms: n out of range");
   CU(cudaSetDevice(h->device));
   CU(cudaStreamSynchronize(h->stream));
   const int st = h->stride;
@@ -737,7 +823,7 @@ int sh_get_pairs(const sh_ctx *hc, int64_t cap, int64_t *npairs, int64_t *tag_i,
 int sh_get_energy(const sh_ctx *hc, double *ke_trans, double *ke_rot, double *e_contact) {
   sh_ctx *h = const_cast<sh_ctx *>(hc);
   CU(cudaSetDevice(h->device));
-  const int n = (int)h->n;
+  const int n = (int)(h->n - h->nghost);
   double kt = 0, kr = 0, ec = 0;
   if (n > 0) {
     int rc = prepare(h);

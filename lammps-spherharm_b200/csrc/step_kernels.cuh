@@ -39,9 +39,11 @@ __device__ __forceinline__ void pose_of(const DevShape &s, const double q[4], co
 
 // pose of every atom; also raises the neighbor-rebuild flag when an SH origin has moved more than
 // sqrt(trigger2) since the last build (trigger2 < 0 disables the check)
-__global__ void pose_kernel(AtomView A, const DevShape *shapes, double trigger2, int *rebuild_flag) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= A.n) return;
+__global__ void pose_kernel(AtomView A, const DevShape *shapes, double trigger2, int *rebuild_flag, int first,
+                            int count) {
+  const int tix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tix >= count) return;
+  const int i = first + tix;
   const int st = A.stride;
   const DevShape &s = shapes[A.shape[i]];
   double q[4] = {A.q[i], A.q[st + i], A.q[2 * st + i], A.q[3 * st + i]};
@@ -58,6 +60,26 @@ __global__ void pose_kernel(AtomView A, const DevShape *shapes, double trigger2,
     disp2 += dd * dd;
   }
   if (trigger2 >= 0 && disp2 > trigger2) *rebuild_flag = 1;
+}
+
+// ghost exchange: record = x(3) + shift(3), quat(4) -> 7 doubles per atom (56 B/ghost)
+__global__ void pack_atoms_kernel(AtomView A, int m, const int *idx, const double *shift, double *out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m) return;
+  const int i = idx[k], st = A.stride;
+#pragma unroll
+  for (int d = 0; d < 3; d++) out[7 * (size_t)k + d] = A.x[d * st + i] + (shift ? shift[3 * (size_t)k + d] : 0.0);
+#pragma unroll
+  for (int d = 0; d < 4; d++) out[7 * (size_t)k + 3 + d] = A.q[d * st + i];
+}
+__global__ void unpack_atoms_kernel(AtomView A, int first, int m, const double *in) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m) return;
+  const int i = first + k, st = A.stride;
+#pragma unroll
+  for (int d = 0; d < 3; d++) A.x[d * st + i] = in[7 * (size_t)k + d];
+#pragma unroll
+  for (int d = 0; d < 4; d++) A.q[d * st + i] = in[7 * (size_t)k + 3 + d];
 }
 
 // AoS (n x ncomp, host layout) <-> SoA (ncomp x stride, device layout) transposes for the C-ABI

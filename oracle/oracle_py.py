@@ -129,7 +129,7 @@ class Oracle:
     def run(self, nsteps):
         self._ck(self.L.orc_run(self.h, C.c_int64(nsteps)))
 
-    def get_atoms(self):
+    def get_atoms(self, fields=None):
         n = self.n
         out = dict(x=np.zeros((n, 3)), v=np.zeros((n, 3)), quat=np.zeros((n, 4)), angmom=np.zeros((n, 3)),
                    f=np.zeros((n, 3)), torque=np.zeros((n, 3)))
