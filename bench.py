@@ -183,15 +183,27 @@ def run_graft(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    # ---- workload: every rank owns an independent replica packing of the same size (weak scaling;
-    # the spatial-decomposition ghost exchange of SURVEY §8e is not built yet — replicas only)
-    cfg = make_workload(args, pkg)
-    n = len(cfg["x"])
+    # ---- workload.  N = 1: the ~100k-particle packing on one GPU.  N > 1: ONE periodic packing of
+    # ~N x 100k particles, spatially decomposed into N bricks (decomp.py): ghost forward exchange over
+    # NCCL every step, migration on rebuild steps ("weak" scaling: fixed work per GPU).
+    dd = None
     sim = pkg.ShGpu(device=local)
-    W.apply(sim, cfg)
-    peak = sim.measure_fp64_peak() if rank == 0 else None
-    sim.compute_forces()
-    sim.run(args.warmup)
+    if use_dist:
+        cfg = make_workload(args, pkg, args.particles * world)
+        D = pkg.load_decomp()
+        dd = D.DomainDecomposition(sim, cfg, comm_device="cuda")
+        n = dd.nlocal
+        peak = sim.measure_fp64_peak() if rank == 0 else None
+        dd.setup()
+        dd.run(args.warmup)
+    else:
+        cfg = make_workload(args, pkg)
+        n = len(cfg["x"])
+        W.apply(sim, cfg)
+        peak = sim.measure_fp64_peak() if rank == 0 else None
+        sim.compute_forces()
+        sim.run(args.warmup)
+    n_global = len(cfg["x"])
     sim.reset_timers()
 
     def barrier():
@@ -204,14 +216,21 @@ def run_graft(args):
     if rank == 0:
         sampler.start()
     t0 = time.perf_counter()
-    sim.run(args.steps)
+    nreb = 0
+    if dd is not None:
+        sim.mark_begin()
+        nreb = dd.run(args.steps)
+        dev_s = sim.mark_end()
+    else:
+        sim.run(args.steps)
+        dev_s = sim.get_run_time()["last"]
     wall = time.perf_counter() - t0
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    dev_s = sim.get_run_time()["last"]
     cnt = sim.get_counters()
     tim = sim.get_timers()
-    pairs_local = cnt["pair_evals"]
+    # a pair that straddles a brick boundary is evaluated by both ranks: count it once (half on each side)
+    pairs_local = cnt["pair_evals"] - 0.5 * sim.get_ghost_pair_evals()
     t_all = torch.tensor([dev_s, wall], dtype=torch.float64, device="cuda")
     p_all = torch.tensor([float(pairs_local), float(n * args.steps)], dtype=torch.float64, device="cuda")
     if use_dist:
@@ -221,11 +240,12 @@ def run_graft(args):
     pairs_total, psteps_total = p_all.tolist()
 
     # ---- e2e: Pair::compute offload through the C-ABI with pinned HOST buffers, copies inside the timed region
-    st = sim.get_atoms(("x", "quat"))
+    st = sim.get_atoms(("x", "quat"))           # owned + ghost atoms of this rank
+    nall = len(st["x"])
     hx = torch.from_numpy(st["x"]).pin_memory()
     hq = torch.from_numpy(st["quat"]).pin_memory()
-    hf = torch.empty((n, 3), dtype=torch.float64).pin_memory()
-    ht = torch.empty((n, 3), dtype=torch.float64).pin_memory()
+    hf = torch.empty((nall, 3), dtype=torch.float64).pin_memory()
+    ht = torch.empty((nall, 3), dtype=torch.float64).pin_memory()
     e2e_steps = max(1, min(args.steps, 20))
     for _ in range(min(3, args.warmup)):
         sim.put_state(x=hx.data_ptr(), quat=hq.data_ptr()); sim.compute_forces(); sim.get_forces(hf.data_ptr(), ht.data_ptr())
@@ -239,7 +259,7 @@ def run_graft(args):
         sim.get_forces(hf.data_ptr(), ht.data_ptr())
     barrier()
     e2e_s = time.perf_counter() - t0
-    e2e_pairs = sim.get_counters()["pair_evals"] - c0
+    e2e_pairs = (sim.get_counters()["pair_evals"] - c0) * (pairs_local / max(1.0, float(cnt["pair_evals"])))
     e_all = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     ep_all = torch.tensor([float(e2e_pairs)], dtype=torch.float64, device="cuda")
     if use_dist:
@@ -269,13 +289,15 @@ def run_graft(args):
         line = {"metric": METRIC, "value": pairs_total / dev_s_max, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * dev_s_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config(args, n),
+                "config": dict(workload_config(args, n_global), parallelism=("single GPU" if world == 1 else
+                               "spatial decomposition %s bricks, NCCL all_to_all ghost exchange every step, %d rebuilds"
+                               % ("x".join(str(v) for v in dd.pgrid), nreb))),
                 "particle_steps_per_s": psteps_total / dev_s_max,
                 "wall_ms_per_step": 1e3 * wall_max / args.steps,
                 "neighbor_builds": cnt["neighbor_builds"],
                 "clocks": clocks,
-                "e2e": {"value": ep_all.item() / e_all.item(), "unit": UNIT, "h2d_bytes_per_step": int(n * 7 * 8),
-                        "d2h_bytes_per_step": int(n * 6 * 8), "steps": e2e_steps,
+                "e2e": {"value": ep_all.item() / e_all.item(), "unit": UNIT, "h2d_bytes_per_step": int(nall * 7 * 8),
+                        "d2h_bytes_per_step": int(nall * 6 * 8), "steps": e2e_steps,
                         "path": "sh_put_state(x,quat pinned host) + sh_compute_forces + sh_get_forces(f,torque pinned host)"},
                 "gpu_launches": int(cnt["kernel_launches"]),
                 "roofline": roofline}

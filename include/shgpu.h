@@ -97,6 +97,8 @@ int sh_get_energy(const sh_ctx *h, double *ke_trans, double *ke_rot, double *e_c
 int sh_get_counters(const sh_ctx *h, int64_t *pair_evals, int64_t *nodes_transformed,
                     int64_t *nodes_evaluated, int64_t *nodes_inside, int64_t *neighbor_builds,
                     int64_t *kernel_launches);
+/* pair evaluations whose second atom is a ghost (each such pair is also evaluated by the owner rank) */
+int sh_get_ghost_pair_evals(const sh_ctx *h, int64_t *ghost_pair_evals);
 /* device time (CUDA events on the library's stream) accumulated since sh_reset_timers ---------- */
 int sh_get_timers(const sh_ctx *h, double *seconds_pair, int64_t *pair_launches,
                   double *seconds_neigh, double *seconds_other);

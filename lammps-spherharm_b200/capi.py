@@ -230,6 +230,11 @@ class ShGpu:
                 "kernel_launches")
         return {k: t.value for k, t in zip(keys, v)}
 
+    def get_ghost_pair_evals(self):
+        v = C.c_int64()
+        self._ck(self.L.sh_get_ghost_pair_evals(self.h, C.byref(v)))
+        return v.value
+
     def get_timers(self):
         sp, sn, so, nl = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
         self._ck(self.L.sh_get_timers(self.h, C.byref(sp), C.byref(nl), C.byref(sn), C.byref(so)))

@@ -39,8 +39,9 @@ struct PairArgs {
   double boxlen[3];
   int periodic[3];
   int *work_counter;
-  unsigned long long *counters;  // [0]=pairs [1]=nodes transformed [2]=evaluated [3]=inside
+  unsigned long long *counters;  // [0]=pairs [1]=nodes transformed [2]=evaluated [3]=inside [4]=pairs with a ghost
   int max_terms, max_nq;      // shared-memory sizing
+  int nlocal;                 // atoms >= nlocal are ghosts (counters[4] counts pairs with a ghost)
 };
 
 __host__ __device__ inline size_t pair_smem_bytes(int max_terms, int max_nq, int nwarps) {
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(NT) pair_kernel(PairArgs A) {
   int *s_int = reinterpret_cast<int *>(s_list + max_chunks * 32);  // [0]=pair [1]=nsurv [2]=loaded shape
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  unsigned long long n_eval = 0, n_inside = 0, n_trans = 0, n_pairs = 0;  // thread 0 only
+  unsigned long long n_eval = 0, n_inside = 0, n_trans = 0, n_pairs = 0, n_gh = 0;  // thread 0 only
   if (tid == 0) s_int[2] = -1;
 
   for (;;) {
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(NT) pair_kernel(PairArgs A) {
 
     // ---- contact law + outputs
     if (tid == 0) {
-      n_pairs++;
+      n_pairs++; n_gh += (j >= A.nlocal);
       const double *Ri_ = A.Rs, *dij = s_dir, *dji = s_dir + 10;
       // rotate body-frame sums to the space frame
       double Sij[3], Tij[3], Gij[3], Sji[3], Tji[3], Gji[3];
@@ -283,6 +284,7 @@ __global__ void __launch_bounds__(NT) pair_kernel(PairArgs A) {
     atomicAdd(&A.counters[1], n_trans);
     atomicAdd(&A.counters[2], n_eval);
     atomicAdd(&A.counters[3], n_inside);
+    atomicAdd(&A.counters[4], n_gh);
   }
 }
 

@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(NW * 32) pair_warp_kernel(PairArgs A, int nsha
   unsigned short *ring = s_ring + warp * 128;
   double *dir0 = s_dir + warp * 10;
   double *pose = s_pose + warp * 16;
-  unsigned long long n_eval = 0, n_inside = 0, n_trans = 0, n_pairs = 0;
+  unsigned long long n_eval = 0, n_inside = 0, n_trans = 0, n_pairs = 0, n_gh = 0;
   const int st = A.stride;
 
   for (;;) {
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(NW * 32) pair_warp_kernel(PairArgs A, int nsha
 
     // ---- contact law + outputs; uniform across the warp, lane 0 stores
     {
-      n_pairs++; n_inside += ninside_pair;
+      n_pairs++; n_inside += ninside_pair; n_gh += (j >= A.nlocal);
       const double dij[10] = {dir0[0], dir0[1], dir0[2], dir0[3], dir0[4], dir0[5], dir0[6], dir0[7], dir0[8], dir0[9]};
       const double dji[10] = {acc.S0, acc.S1, acc.S2, acc.A, acc.T0, acc.T1, acc.T2, acc.G0, acc.G1, acc.G2};
       double Sij[3], Tij[3], Gij[3], Sji[3], Tji[3], Gji[3];
@@ -341,6 +341,7 @@ __global__ void __launch_bounds__(NW * 32) pair_warp_kernel(PairArgs A, int nsha
     atomicAdd(&A.counters[1], n_trans);
     atomicAdd(&A.counters[2], n_eval);
     atomicAdd(&A.counters[3], n_inside);
+    atomicAdd(&A.counters[4], n_gh);
   }
 }
 

@@ -336,7 +336,7 @@ int compute_forces_device(sh_ctx *h) {
     P.work_counter = h->scalars.p + 2; P.counters = h->counters.p;
     int maxT = 1, maxq = 32;
     for (auto &s : h->shapes) { maxT = std::max(maxT, s.nterms); maxq = std::max(maxq, s.nq); }
-    P.max_terms = maxT; P.max_nq = maxq;
+    P.max_terms = maxT; P.max_nq = maxq; P.nlocal = n;
     CU(cudaMemsetAsync(h->scalars.p + 2, 0, sizeof(int), h->stream));
     const int nt = h->tune_threads ? h->tune_threads : 128;
     if (h->ev_used + 2 > h->ev.size()) { if (drain_events(h)) return -2; }
@@ -850,6 +850,16 @@ int sh_get_energy(const sh_ctx *hc, double *ke_trans, double *ke_rot, double *e_
   if (ke_trans) *ke_trans = kt;
   if (ke_rot) *ke_rot = kr;
   if (e_contact) *e_contact = ec;
+  return 0;
+}
+
+int sh_get_ghost_pair_evals(const sh_ctx *hc, int64_t *ghost_pair_evals) {
+  sh_ctx *h = const_cast<sh_ctx *>(hc);
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  unsigned long long c = 0;
+  CU(cudaMemcpy(&c, h->counters.p + 4, sizeof c, cudaMemcpyDeviceToHost));
+  if (ghost_pair_evals) *ghost_pair_evals = (int64_t)c;
   return 0;
 }
 

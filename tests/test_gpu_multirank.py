@@ -19,8 +19,8 @@ pkg = shpkg.load(); W = pkg.workloads; D = pkg.load_decomp()
 local = int(os.environ["LOCAL_RANK"]); torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 rank, world = dist.get_rank(), dist.get_world_size()
-cfg = W.packing((6, 4, 4), 20, (32, 64), nshapes=4, seed=21, periodic=True, name="mr", skin=0.08, vel_sigma=0.5, dt=2e-4)
-nsteps = 150
+cfg = W.packing((6, 4, 4), 20, (32, 64), nshapes=4, seed=21, periodic=True, name="mr", skin=0.03, vel_sigma=0.5, dt=4e-4)
+nsteps = 300
 dd = D.DomainDecomposition(pkg.ShGpu(device=local), cfg, comm_device="cuda")
 dd.setup()
 f0 = dd.gather_owned(("f", "torque"))
