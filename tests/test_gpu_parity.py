@@ -174,6 +174,41 @@ def test_deep_overlap_and_poles():
         g.close(); o.close()
 
 
+def test_lmax50_tables_in_global_memory():
+    """configs[4] at reduced size: l_max=50, 80x160 quadrature, 8 shapes -> 255 KB of folded tables do not
+    fit in shared memory, the pair kernel reads them through L1/L2 instead (SMEM_TABLES=false path)."""
+    cfg = W.packing((2, 2, 2), 50, (80, 160), nshapes=8, seed=50, nn_frac=1.8, name="l50")
+    g, o = both(cfg, threads=16)
+    e = check_forces(g, o)
+    assert e["ncontact"] > 10
+    print("l50:", e)
+
+
+def test_mixed_lmax_shapes():
+    """Shapes with different l_max in one system (tables of different length, same quadrature)."""
+    a1, b1 = W.ellipsoid_shape(8)
+    a2, b2 = W.perturbed_shape(20, 3)
+    a3, b3 = W.sphere_shape(0, 0.9)
+    rng = np.random.default_rng(4)
+    pos, box = W.fcc_positions((3, 3, 3), 1.75)
+    n = len(pos)
+    sims = []
+    for mk in (lambda: pkg.ShGpu(), lambda: O.Oracle(threads=8)):
+        s = mk()
+        s.set_box(np.zeros(3), box, (1, 1, 1)); s.set_quadrature(32, 64)
+        ids = [s.add_shape(8, a1, b1, 1.0), s.add_shape(20, a2, b2, 1.3), s.add_shape(0, a3, b3, 0.7)]
+        sims.append(s)
+    sid = rng.integers(0, 3, size=n).astype(np.int32)
+    q = W.random_quaternions(rng, n)
+    for s in sims:
+        s.set_atoms(sid, pos, None, q, None)
+        for i in range(3):
+            for j in range(i, 3):
+                s.pair_coeff(i, j, 500.0 * (1 + i + j), 1.0 + 0.25 * ((i + j) % 2))
+    e = check_forces(sims[0], sims[1])
+    assert e["ncontact"] > 20
+
+
 def test_error_paths():
     g = pkg.ShGpu()
     with pytest.raises(pkg.ShGpuError):
