@@ -49,6 +49,23 @@ def build(force=False, verbose=False):
     return SO
 
 
+SHLMP = os.path.join(HERE, "shlmp")
+
+
+def build_host(force=False):
+    """Compile the shlmp input-script front-end (plain C++, links libshgpu.so)."""
+    src = os.path.join(HERE, "host", "shlmp.cpp")
+    if not force and os.path.exists(SHLMP) and os.path.getmtime(SHLMP) > max(os.path.getmtime(src), os.path.getmtime(SO)):
+        return SHLMP
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    cmd = [gxx, "-O2", "-std=c++17", "-o", SHLMP, src, "-L" + HERE, "-lshgpu", "-Wl,-rpath,$ORIGIN"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
+    return SHLMP
+
+
 if __name__ == "__main__":
     import sys
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_host(force="--force" in sys.argv))
