@@ -24,6 +24,8 @@ struct DevShape {
   int tab_off;                            // offset (in records) of this shape in the concatenated table
   int nterms4;                            // nterms rounded up to a multiple of 4; tables hold nterms4+4 records
   const float *row_x;                     // cos(theta_row), float copy for the conservative window
+  const float *cube_b2;                   // conservative r^2 upper bound per cube-map direction cell (6*cube_n^2)
+  int cube_n, pad2_;
 };
 
 // rotation matrix (row-major R[3*r+c]) of unit quaternion (w,x,y,z); plain mul/add, fixed order

@@ -3,6 +3,7 @@
 // Compiled with -ffp-contract=off; no fused operations on this path.
 #include "shape_tables.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -135,6 +136,70 @@ void fold_recurrence(ShapeTables &s) {
       s.bh[idx] = (m == 0) ? 0.0 : (s.b_raw[k] * alpha[l]) * cm;
     }
     o += L + 1 - m;
+  }
+}
+
+// r(direction) with the folded tables; plain a*b+c arithmetic (bounds only, not the decision path)
+double radius_for_bounds(const ShapeTables &s, double s0, double s1, double s2) {
+  const int L = s.lmax;
+  const double rho = std::sqrt(s0 * s0 + s1 * s1 + s2 * s2), inv = 1.0 / rho;
+  const double x = s2 * inv, zx = s0 * inv, zy = s1 * inv;
+  double u = 1.0, v = 0.0, r = 0.0;
+  int base = 0;
+  for (int m = 0; m <= L; m++) {
+    if (m > 0) { const double un = u * zx - v * zy, vn = u * zy + v * zx; u = un; v = vn; }
+    double C = s.ah[base], S = s.bh[base];
+    if (m < L) {
+      double q1 = s.Ap[base + 1] * x, q2 = 1.0;
+      C += s.ah[base + 1] * q1; S += s.bh[base + 1] * q1;
+      for (int i = 2; i <= L - m; i++) {
+        const double q = s.Ap[base + i] * x * q1 - q2;
+        C += s.ah[base + i] * q; S += s.bh[base + i] * q;
+        q2 = q1; q1 = q;
+      }
+    }
+    r += u * C + v * S;
+    base += L + 1 - m;
+  }
+  return r;
+}
+
+// cube-map direction cells: face f in 0..5 = +x,-x,+y,-y,+z,-z; (u,v) = the two other components (in x,y,z
+// order) divided by |major|; cell (iu,iv) = floor((u+1)/2*n).  Samples overlap one sub-step into the
+// neighbouring cells / faces and the bound is padded by the largest adjacent-sample difference, so that an
+// FP32 cell index (pair_warp_kernel.cuh) that lands in a neighbouring cell near a border is still covered.
+void build_cube_bounds(ShapeTables &s, int n, int sub) {
+  s.cube_n = n;
+  s.cube_bound2.assign((size_t)6 * n * n, 0.0f);
+  const int ns = n * sub + 3;                  // samples per face edge: indices -1 .. n*sub+1
+  std::vector<double> r((size_t)ns * ns);
+  for (int f = 0; f < 6; f++) {
+    const int major = f / 2;
+    const double sgn = (f % 2) ? -1.0 : 1.0;
+    for (int a = 0; a < ns; a++)
+      for (int b = 0; b < ns; b++) {
+        const double u = -1.0 + 2.0 * (a - 1) / (double)(n * sub), v = -1.0 + 2.0 * (b - 1) / (double)(n * sub);
+        double d[3];
+        d[major] = sgn;
+        d[major == 0 ? 1 : 0] = u;
+        d[major == 2 ? 1 : 2] = v;
+        r[(size_t)a * ns + b] = radius_for_bounds(s, d[0], d[1], d[2]);
+      }
+    for (int iu = 0; iu < n; iu++)
+      for (int iv = 0; iv < n; iv++) {
+        double mx = 0, dmax = 0;
+        for (int a = iu * sub; a <= (iu + 1) * sub + 2; a++)
+          for (int b = iv * sub; b <= (iv + 1) * sub + 2; b++) {
+            const double v0 = r[(size_t)a * ns + b];
+            mx = std::max(mx, v0);
+            if (a + 1 < ns) dmax = std::max(dmax, std::fabs(r[(size_t)(a + 1) * ns + b] - v0));
+            if (b + 1 < ns) dmax = std::max(dmax, std::fabs(r[(size_t)a * ns + b + 1] - v0));
+          }
+        const double bound = (mx + dmax) * (1.0 + 1e-6);
+        float b2 = (float)(bound * bound);
+        b2 = std::nextafter(b2, 3.0e38f);      // round up: the FP32 value must not be below the FP64 bound^2
+        s.cube_bound2[((size_t)f * n + iu) * n + iv] = b2;
+      }
   }
 }
 
@@ -273,6 +338,7 @@ std::string build_shape_tables(int lmax, const double *a_lm, const double *b_lm,
   quat_from_rotation(V, qp);
   for (int d = 0; d < 4; d++) s.quat_principal[d] = qp[d];
   rotation_from_quat(qp, s.Rp);
+  build_cube_bounds(s, 24, 6);
   return "";
 }
 

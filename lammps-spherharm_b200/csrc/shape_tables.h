@@ -21,6 +21,10 @@ struct ShapeTables {
   std::vector<double> ah, bh;            // coefficients with alpha_lm * c_m folded in
   // node table, SoA: px,py,pz, nx,ny,nz (oriented area elements n dS)
   std::vector<double> node_p[3], node_n[3];
+  // conservative squared upper bound of r over the cells of a cube map of directions (6 x cube_n x cube_n):
+  // a node with rho^2 >= bound2(cell(direction)) is certainly outside, no SH evaluation needed
+  int cube_n = 0;
+  std::vector<float> cube_bound2;
   std::vector<double> row_x;             // cos(theta) of the Gauss-Legendre rows (node k = row*n_phi+col)
   double density = 1, volume = 0, mass = 0;
   std::array<double, 3> com{}, inertia{};

@@ -41,7 +41,7 @@ struct DevBuf {
 struct ShapeDev {
   DevBuf<double> Ap, node;   // node: 6 x nq
   DevBuf<double2> ab;
-  DevBuf<float> row_x;
+  DevBuf<float> row_x, cube;
 };
 
 }  // namespace
@@ -131,6 +131,8 @@ int upload_shapes(sh_ctx *h) {
       {
         std::vector<float> rx(t.row_x.begin(), t.row_x.end());
         CU(cudaMemcpy(d.row_x.p, rx.data(), rx.size() * sizeof(float), cudaMemcpyHostToDevice));
+        d.cube.ensure(t.cube_bound2.size());
+        CU(cudaMemcpy(d.cube.p, t.cube_bound2.data(), t.cube_bound2.size() * sizeof(float), cudaMemcpyHostToDevice));
       }
       std::vector<double2> ab(t.nterms);
       for (int k = 0; k < t.nterms; k++) ab[k] = make_double2(t.ah[k], t.bh[k]);
@@ -149,7 +151,7 @@ int upload_shapes(sh_ctx *h) {
       v.Ap = d.Ap.p; v.ab = d.ab.p;
       v.px = d.node.p; v.py = d.node.p + t.nq; v.pz = d.node.p + 2 * (size_t)t.nq;
       v.nx = d.node.p + 3 * (size_t)t.nq; v.ny = d.node.p + 4 * (size_t)t.nq; v.nz = d.node.p + 5 * (size_t)t.nq;
-      v.n_theta = t.n_theta; v.n_phi = t.n_phi; v.nterms4 = (t.nterms + 3) / 4 * 4; v.row_x = d.row_x.p;
+      v.n_theta = t.n_theta; v.n_phi = t.n_phi; v.nterms4 = (t.nterms + 3) / 4 * 4; v.row_x = d.row_x.p; v.cube_b2 = d.cube.p; v.cube_n = t.cube_n; v.pad2_ = 0;
     }
     int off = 0;
     for (int s = 0; s < ns; s++) { h->shape_host_view[s].tab_off = off; off += h->shape_host_view[s].nterms4 + 4; }
@@ -317,7 +319,7 @@ int launch_pair_warp(sh_ctx *h, const PairArgs &A, int ctas_per_sm) {
   if (occ < 1) return fail(h, "pair warp kernel does not fit on an SM");
   if (ctas_per_sm > 0) occ = std::min(occ, ctas_per_sm);
   const int grid = std::max(1, std::min((A.npairs + NW - 1) / NW, occ * h->sm_count));
-  pair_warp_kernel<NW, SMEM_TABLES><<<grid, NW * 32, smem, h->stream>>>(A, (int)h->shapes.size(), h->total_terms);
+  pair_warp_kernel<NW, SMEM_TABLES><<<grid, NW * 32, smem, h->stream>>>(A, (int)h->shapes.size(), h->total_terms, (h->tune_variant & 2) ? 0 : 1);
   return 0;
 }
 
@@ -342,7 +344,7 @@ int compute_forces_device(sh_ctx *h) {
     if (h->ev_used + 2 > h->ev.size()) { if (drain_events(h)) return -2; }
     CU(cudaEventRecord(h->ev[h->ev_used], h->stream));
     int rc;
-    if (h->tune_variant == 1) {          // CTA-per-pair kernel (full-table scan)
+    if (h->tune_variant & 1) {           // CTA-per-pair kernel (full-table scan)
       if (nt == 256) rc = launch_pair<256>(h, P, h->tune_ctas_per_sm, pair_smem_bytes(maxT, maxq, 8));
       else if (nt == 64) rc = launch_pair<64>(h, P, h->tune_ctas_per_sm, pair_smem_bytes(maxT, maxq, 2));
       else rc = launch_pair<128>(h, P, h->tune_ctas_per_sm, pair_smem_bytes(maxT, maxq, 4));
@@ -440,7 +442,7 @@ int sh_destroy(sh_ctx *h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  for (auto &d : h->shape_dev) { d.Ap.release(); d.ab.release(); d.node.release(); d.row_x.release(); }
+  for (auto &d : h->shape_dev) { d.Ap.release(); d.ab.release(); d.node.release(); d.row_x.release(); d.cube.release(); }
   h->d_shapes.release(); h->d_pk.release(); h->d_pm.release();
   DevBuf<double> *db[] = {&h->x, &h->v, &h->q, &h->L, &h->f, &h->tq, &h->c, &h->Rs, &h->c0, &h->wallf, &h->ewall, &h->ke, &h->bbox, &h->slot, &h->pres};
   for (auto *b : db) b->release();

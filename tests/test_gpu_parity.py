@@ -30,10 +30,12 @@ def check_forces(g, o, tol=TOL):
     g.compute_forces()
     o.compute_forces()
     cg, co = g.get_counters(), o.get_counters()
-    for k in ("pair_evals", "nodes_evaluated", "nodes_inside"):
+    for k in ("pair_evals", "nodes_inside"):
         assert cg[k] == co[k], (k, cg[k], co[k])
-    # the GPU's conservative window visits a subset of the nodes the oracle's full scan transforms
+    # the GPU's conservative window / direction-cell bound visit and evaluate a SUBSET of the nodes the
+    # oracle's full scan transforms and evaluates; the set of inside nodes must be identical
     assert cg["nodes_transformed"] <= co["nodes_transformed"]
+    assert cg["nodes_evaluated"] <= co["nodes_evaluated"]
     e = pair_rel_errors(g.get_pairs(), o.get_pairs())
     assert e["V"] <= tol and e["F"] <= tol and e["tau"] <= tol and e["centroid"] <= tol, e
     ag, ao = g.get_atoms(), o.get_atoms()
@@ -149,7 +151,7 @@ def test_neighbor_skin_does_not_change_forces():
     assert np.abs(res[0] - res[1]).max() <= 1e-12 * np.abs(res[0]).max()
 
 
-@pytest.mark.parametrize("threads,variant", [(128, 1), (256, 1), (128, 0), (256, 0), (384, 0), (512, 0)])
+@pytest.mark.parametrize("threads,variant", [(128, 1), (256, 1), (128, 0), (256, 0), (384, 0), (512, 0), (512, 2)])
 def test_kernel_variants_agree_with_oracle(threads, variant):
     """CTA-per-pair full-scan kernel (variant 1) and warp-per-pair windowed kernel (variant 0)."""
     cfg = W.config3_packing(256, lmax=20, grid=(32, 64))
@@ -157,8 +159,12 @@ def test_kernel_variants_agree_with_oracle(threads, variant):
     g.set_pair_tuning(threads, 0, variant)
     e = check_forces(g, o)
     assert e["ncontact"] > 20
-    if variant == 1:
+    if variant == 1:      # full scan: every counter equals the oracle's
         assert g.get_counters()["nodes_transformed"] == o.get_counters()["nodes_transformed"]
+    if variant in (1, 2):  # no direction-cell bound: every bounding-sphere survivor is evaluated, as in the oracle
+        assert g.get_counters()["nodes_evaluated"] == o.get_counters()["nodes_evaluated"]
+    if variant == 0:
+        assert g.get_counters()["nodes_evaluated"] < o.get_counters()["nodes_evaluated"]
 
 
 def test_deep_overlap_and_poles():
