@@ -103,6 +103,10 @@ int sh_get_ghost_pair_evals(const sh_ctx *h, int64_t *ghost_pair_evals);
 int sh_get_timers(const sh_ctx *h, double *seconds_pair, int64_t *pair_launches,
                   double *seconds_neigh, double *seconds_other);
 int sh_reset_timers(sh_ctx *h);
+/* split pair pipeline: device time of the SH-evaluation kernel, its launches, pairs routed to the fused
+ * deep-contact kernel, survivor-pool regrowths */
+int sh_get_split_stats(const sh_ctx *h, double *seconds_eval, int64_t *eval_launches, int64_t *deep_pairs,
+                       int64_t *pool_redos);
 /* device time of sh_run (events on the library's stream bracketing all steps of the call) -------- */
 int sh_get_run_time(const sh_ctx *h, double *seconds_last_run, double *seconds_total);
 

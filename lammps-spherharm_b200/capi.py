@@ -240,6 +240,11 @@ class ShGpu:
         self._ck(self.L.sh_get_timers(self.h, C.byref(sp), C.byref(nl), C.byref(sn), C.byref(so)))
         return dict(seconds_pair=sp.value, pair_launches=nl.value, seconds_neigh=sn.value, seconds_other=so.value)
 
+    def get_split_stats(self):
+        a, b, c, d = C.c_double(), C.c_int64(), C.c_int64(), C.c_int64()
+        self._ck(self.L.sh_get_split_stats(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return dict(seconds_eval=a.value, eval_launches=b.value, deep_pairs=c.value, pool_redos=d.value)
+
     def reset_timers(self):
         self._ck(self.L.sh_reset_timers(self.h))
 

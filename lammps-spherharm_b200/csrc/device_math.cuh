@@ -26,6 +26,7 @@ struct DevShape {
   const float *row_x;                     // cos(theta_row), float copy for the conservative window
   const float *cube_b2;                   // conservative r^2 upper bound per cube-map direction cell (6*cube_n^2)
   int cube_n, pad2_;
+  const float *pf;                        // FP32 copy of the node points (3 x nq, SoA) for the conservative pre-cull
 };
 
 // rotation matrix (row-major R[3*r+c]) of unit quaternion (w,x,y,z); plain mul/add, fixed order

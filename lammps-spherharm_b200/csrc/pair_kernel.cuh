@@ -42,6 +42,7 @@ struct PairArgs {
   unsigned long long *counters;  // [0]=pairs [1]=nodes transformed [2]=evaluated [3]=inside [4]=pairs with a ghost
   int max_terms, max_nq;      // shared-memory sizing
   int nlocal;                 // atoms >= nlocal are ghosts (counters[4] counts pairs with a ghost)
+  const int *pair_list;       // optional indirection: process pairs pair_list[0..npairs) (deep-contact list)
 };
 
 __host__ __device__ inline size_t pair_smem_bytes(int max_terms, int max_nq, int nwarps) {
@@ -76,8 +77,8 @@ __global__ void __launch_bounds__(NT) pair_kernel(PairArgs A) {
   for (;;) {
     if (tid == 0) s_int[0] = atomicAdd(A.work_counter, 1);
     __syncthreads();
-    const int p = s_int[0];
-    if (p >= A.npairs) break;
+    if (s_int[0] >= A.npairs) break;
+    const int p = A.pair_list ? A.pair_list[s_int[0]] : s_int[0];
     const int i = A.pair_i[p], j = A.pair_j[p];
     const int st = A.stride;
     // minimum-image separation d = c_i - c_j (same ops as the oracle)

@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(NW * 32) pair_warp_kernel(PairArgs A, int nsha
     if (lane == 0) p = atomicAdd(A.work_counter, 1);
     p = __shfl_sync(0xffffffffu, p, 0);
     if (p >= A.npairs) break;
+    if (A.pair_list) p = A.pair_list[p];
     const int i = A.pair_i[p], j = A.pair_j[p];
     double d[3];
 #pragma unroll

@@ -17,6 +17,7 @@
 #include "neighbor_kernels.cuh"
 #include "pair_kernel.cuh"
 #include "pair_warp_kernel.cuh"
+#include "pair_split_kernels.cuh"
 #include "shape_tables.h"
 #include "step_kernels.cuh"
 
@@ -41,7 +42,7 @@ struct DevBuf {
 struct ShapeDev {
   DevBuf<double> Ap, node;   // node: 6 x nq
   DevBuf<double2> ab;
-  DevBuf<float> row_x, cube;
+  DevBuf<float> row_x, cube, pf;
 };
 
 }  // namespace
@@ -78,6 +79,17 @@ struct sh_ctx {
   DevBuf<int> cell_of, cell_count, cell_start, cell_fill, cell_atoms, tile_sum, cnt_full, cnt_half, nbr_off, half_off,
       nbr_j, pair_i, pair_j, pair_eij, pair_eji, scalars;  // scalars: [0]=total [1]=rebuild flag [2]=work counter
   DevBuf<double> bbox, slot, pres, stage;
+  // split pair pipeline (pair_split_kernels.cuh)
+  DevBuf<SurvRec> pool;
+  DevBuf<long long> pool_base, pool_cap, pd_off;
+  DevBuf<unsigned long long> pool_count;
+  DevBuf<int> pd_cnt, big_list, split_flags;   // split_flags: [0]=nbig [1]=overflow
+  std::vector<long long> h_pool_cap;
+  unsigned long long *h_pool_count = nullptr;  // pinned: [nshape] counts, then nbig, overflow
+  cudaEvent_t ev_b0 = nullptr, ev_b1 = nullptr;
+  double sec_eval = 0, sec_cull = 0; int64_t eval_launches = 0;
+  int64_t big_pairs = 0, split_redo = 0;
+  bool eval_pending = false;
   DevBuf<unsigned long long> counters;
   int npairs = 0, nentries = 0;
   int slot_stride = 0, pres_stride = 0;
@@ -86,8 +98,8 @@ struct sh_ctx {
   int64_t steps_since_build = 0;
   // stats
   int64_t neighbor_builds = 0, kernel_launches = 0;
-  std::vector<cudaEvent_t> ev;  // pairs of (start,stop) for the pair kernel
-  size_t ev_used = 0;
+  std::vector<cudaEvent_t> ev, ev2;  // pairs of (start,stop): whole pair phase / evaluation kernel
+  size_t ev_used = 0, ev2_used = 0;
   double sec_pair = 0, sec_neigh = 0, sec_other = 0, sec_run_last = 0, sec_run_total = 0;
   cudaEvent_t run_e0 = nullptr, run_e1 = nullptr;
   int64_t pair_launches = 0;
@@ -131,6 +143,10 @@ int upload_shapes(sh_ctx *h) {
       {
         std::vector<float> rx(t.row_x.begin(), t.row_x.end());
         CU(cudaMemcpy(d.row_x.p, rx.data(), rx.size() * sizeof(float), cudaMemcpyHostToDevice));
+        std::vector<float> pf((size_t)3 * t.nq);
+        for (int e = 0; e < 3; e++) for (int k = 0; k < t.nq; k++) pf[(size_t)e * t.nq + k] = (float)t.node_p[e][k];
+        d.pf.ensure(pf.size());
+        CU(cudaMemcpy(d.pf.p, pf.data(), pf.size() * sizeof(float), cudaMemcpyHostToDevice));
         d.cube.ensure(t.cube_bound2.size());
         CU(cudaMemcpy(d.cube.p, t.cube_bound2.data(), t.cube_bound2.size() * sizeof(float), cudaMemcpyHostToDevice));
       }
@@ -151,7 +167,7 @@ int upload_shapes(sh_ctx *h) {
       v.Ap = d.Ap.p; v.ab = d.ab.p;
       v.px = d.node.p; v.py = d.node.p + t.nq; v.pz = d.node.p + 2 * (size_t)t.nq;
       v.nx = d.node.p + 3 * (size_t)t.nq; v.ny = d.node.p + 4 * (size_t)t.nq; v.nz = d.node.p + 5 * (size_t)t.nq;
-      v.n_theta = t.n_theta; v.n_phi = t.n_phi; v.nterms4 = (t.nterms + 3) / 4 * 4; v.row_x = d.row_x.p; v.cube_b2 = d.cube.p; v.cube_n = t.cube_n; v.pad2_ = 0;
+      v.n_theta = t.n_theta; v.n_phi = t.n_phi; v.nterms4 = (t.nterms + 3) / 4 * 4; v.row_x = d.row_x.p; v.cube_b2 = d.cube.p; v.cube_n = t.cube_n; v.pad2_ = 0; v.pf = d.pf.p;
     }
     int off = 0;
     for (int s = 0; s < ns; s++) { h->shape_host_view[s].tab_off = off; off += h->shape_host_view[s].nterms4 + 4; }
@@ -287,8 +303,14 @@ int build_neighbors(sh_ctx *h) {
 }
 
 int drain_events(sh_ctx *h) {
-  if (h->ev_used == 0) return 0;
+  if (h->ev_used == 0 && h->ev2_used == 0) return 0;
   CU(cudaStreamSynchronize(h->stream));
+  for (size_t k = 0; k + 1 < h->ev2_used; k += 2) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev2[k], h->ev2[k + 1]);
+    h->sec_eval += ms * 1e-3;
+  }
+  h->ev2_used = 0;
   for (size_t k = 0; k + 1 < h->ev_used; k += 2) {
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev[k], h->ev[k + 1]);
@@ -323,6 +345,97 @@ int launch_pair_warp(sh_ctx *h, const PairArgs &A, int ctas_per_sm) {
   return 0;
 }
 
+int launch_fused(sh_ctx *h, const PairArgs &P) {
+  const bool fits = pair_warp_smem_bytes(h->total_terms, 16, true) <= 200 * 1024;
+  const int tw = h->tune_threads ? h->tune_threads : 512;
+  if (fits) {
+    if (tw == 256) return launch_pair_warp<8, true>(h, P, h->tune_ctas_per_sm);
+    if (tw == 128) return launch_pair_warp<4, true>(h, P, h->tune_ctas_per_sm);
+    if (tw == 384) return launch_pair_warp<12, true>(h, P, h->tune_ctas_per_sm);
+    return launch_pair_warp<16, true>(h, P, h->tune_ctas_per_sm);
+  }
+  if (tw == 256) return launch_pair_warp<8, false>(h, P, h->tune_ctas_per_sm);
+  return launch_pair_warp<16, false>(h, P, h->tune_ctas_per_sm);
+}
+
+// cull -> (host reads the pool counters) -> evaluate -> reduce (+ fused kernel on the deep-contact list)
+int run_split_pipeline(sh_ctx *h, PairArgs &P) {
+  const int ns = (int)h->shapes.size(), np = P.npairs;
+  constexpr int WPB = 8;
+  try {
+    h->pd_off.ensure((size_t)2 * np + 2); h->pd_cnt.ensure((size_t)2 * np + 2); h->big_list.ensure(np + 1);
+    h->pool_base.ensure(SH_MAX_SHAPES); h->pool_cap.ensure(SH_MAX_SHAPES); h->pool_count.ensure(SH_MAX_SHAPES); h->split_flags.ensure(4);
+  } catch (std::string &e) { return fail(h, e); }
+  if (!h->h_pool_count) CU(cudaMallocHost(&h->h_pool_count, (SH_MAX_SHAPES + 2) * sizeof(unsigned long long)));
+  if ((int)h->h_pool_cap.size() != ns) {   // first sizing: 16 records per pair-direction, spread over the shapes
+    h->h_pool_cap.assign(ns, std::max<long long>(4096, (long long)np * 32 / std::max(1, ns) * 2));
+  }
+  for (int attempt = 0; attempt < 6; attempt++) {
+    std::vector<long long> base(ns);
+    long long tot = 0;
+    for (int s = 0; s < ns; s++) { base[s] = tot; tot += h->h_pool_cap[s]; }
+    try { h->pool.ensure((size_t)tot + 64); } catch (std::string &e) { return fail(h, e); }
+    CU(cudaMemcpyAsync(h->pool_base.p, base.data(), ns * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->pool_cap.p, h->h_pool_cap.data(), ns * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemsetAsync(h->pool_count.p, 0, SH_MAX_SHAPES * sizeof(unsigned long long), h->stream));
+    CU(cudaMemsetAsync(h->split_flags.p, 0, 4 * sizeof(int), h->stream));
+    SplitArgs S;
+    S.pool = h->pool.p; S.pool_base = h->pool_base.p; S.pool_cap = h->pool_cap.p; S.pool_count = h->pool_count.p;
+    S.pd_off = h->pd_off.p; S.pd_cnt = h->pd_cnt.p; S.big_list = h->big_list.p; S.nbig = h->split_flags.p; S.overflow = h->split_flags.p + 1;
+    CU(cudaMemcpyAsync(h->counters.p + 8, h->counters.p, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, h->stream));
+    pair_cull_kernel<WPB><<<cdiv(np, WPB), WPB * 32, 0, h->stream>>>(P, S, (h->tune_variant & 2) ? 0 : 1);
+    h->kernel_launches++;
+    CU(cudaMemcpyAsync(h->h_pool_count, h->pool_count.p, ns * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(h->h_pool_count + SH_MAX_SHAPES, h->split_flags.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    const int *fl = reinterpret_cast<const int *>(h->h_pool_count + SH_MAX_SHAPES);
+    const int nbig = fl[0], overflow = fl[1];
+    if (overflow) {   // grow the pools to what this step asked for (+50 %) and redo the cull
+      for (int s = 0; s < ns; s++) h->h_pool_cap[s] = std::max<long long>(h->h_pool_cap[s], (long long)(h->h_pool_count[s] * 3 / 2) + 4096);
+      // the cull kernel already added its pair / transform counters: restore the snapshot before the redo
+      CU(cudaMemcpyAsync(h->counters.p, h->counters.p + 8, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, h->stream));
+      h->split_redo++;
+      continue;
+    }
+    // ---- B
+    EvalPlan plan;
+    plan.nshape = ns;
+    int nblk = 0, maxT = 1;
+    for (int s = 0; s < ns; s++) {
+      plan.blk_start[s] = nblk;
+      plan.count[s] = (long long)h->h_pool_count[s];
+      nblk += (int)((plan.count[s] + 64 * WPB - 1) / (64 * WPB));
+      maxT = std::max(maxT, h->shape_host_view[s].nterms4 + 4);
+    }
+    plan.blk_start[ns] = nblk;
+    if (nblk > 0) {
+      const size_t smem = (size_t)maxT * 24 + 32;
+      CU(cudaFuncSetAttribute(pair_eval_kernel<WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+      if (h->ev2_used + 2 > h->ev2.size()) { if (drain_events(h)) return -2; }
+      CU(cudaEventRecord(h->ev2[h->ev2_used], h->stream));
+      pair_eval_kernel<WPB><<<nblk, WPB * 32, smem, h->stream>>>(h->d_shapes.p, S, plan, h->counters.p);
+      CU(cudaEventRecord(h->ev2[h->ev2_used + 1], h->stream));
+      h->ev2_used += 2;
+      h->kernel_launches++; h->eval_launches++;
+    }
+    // ---- C
+    pair_reduce_kernel<<<cdiv(np, 128), 128, 0, h->stream>>>(P, S);
+    h->kernel_launches++;
+    // ---- deep contacts
+    if (nbig > 0) {
+      PairArgs Pb = P;
+      Pb.pair_list = h->big_list.p; Pb.npairs = nbig;
+      CU(cudaMemsetAsync(h->scalars.p + 2, 0, sizeof(int), h->stream));
+      int rc = launch_fused(h, Pb);
+      if (rc) return rc;
+      h->kernel_launches++;
+      h->big_pairs += nbig;
+    }
+    return 0;
+  }
+  return fail(h, "survivor pool kept overflowing");
+}
+
 int compute_forces_device(sh_ctx *h) {
   const int n = (int)(h->n - h->nghost);   // forces are accumulated on owned atoms only
   if (n == 0) { h->forces_valid = true; return 0; }
@@ -338,7 +451,7 @@ int compute_forces_device(sh_ctx *h) {
     P.work_counter = h->scalars.p + 2; P.counters = h->counters.p;
     int maxT = 1, maxq = 32;
     for (auto &s : h->shapes) { maxT = std::max(maxT, s.nterms); maxq = std::max(maxq, s.nq); }
-    P.max_terms = maxT; P.max_nq = maxq; P.nlocal = n;
+    P.max_terms = maxT; P.max_nq = maxq; P.nlocal = n; P.pair_list = nullptr;
     CU(cudaMemsetAsync(h->scalars.p + 2, 0, sizeof(int), h->stream));
     const int nt = h->tune_threads ? h->tune_threads : 128;
     if (h->ev_used + 2 > h->ev.size()) { if (drain_events(h)) return -2; }
@@ -348,18 +461,10 @@ int compute_forces_device(sh_ctx *h) {
       if (nt == 256) rc = launch_pair<256>(h, P, h->tune_ctas_per_sm, pair_smem_bytes(maxT, maxq, 8));
       else if (nt == 64) rc = launch_pair<64>(h, P, h->tune_ctas_per_sm, pair_smem_bytes(maxT, maxq, 2));
       else rc = launch_pair<128>(h, P, h->tune_ctas_per_sm, pair_smem_bytes(maxT, maxq, 4));
-    } else {                             // warp-per-pair kernel (default)
-      const bool fits = pair_warp_smem_bytes(h->total_terms, 16, true) <= 200 * 1024;
-      const int tw = h->tune_threads ? h->tune_threads : 512;
-      if (fits) {
-        if (tw == 256) rc = launch_pair_warp<8, true>(h, P, h->tune_ctas_per_sm);
-        else if (tw == 128) rc = launch_pair_warp<4, true>(h, P, h->tune_ctas_per_sm);
-        else if (tw == 384) rc = launch_pair_warp<12, true>(h, P, h->tune_ctas_per_sm);
-        else rc = launch_pair_warp<16, true>(h, P, h->tune_ctas_per_sm);
-      } else {
-        if (tw == 256) rc = launch_pair_warp<8, false>(h, P, h->tune_ctas_per_sm);
-        else rc = launch_pair_warp<16, false>(h, P, h->tune_ctas_per_sm);
-      }
+    } else if (h->tune_variant & 4) {    // fused warp-per-pair kernel
+      rc = launch_fused(h, P);
+    } else {                             // split pipeline (default): cull / evaluate / reduce
+      rc = run_split_pipeline(h, P);
     }
     if (rc) return rc;
     CU(cudaEventRecord(h->ev[h->ev_used + 1], h->stream));
@@ -426,14 +531,15 @@ int sh_create(sh_ctx **out, int device_id) {
   h->pk.assign(SH_MAX_SHAPES * SH_MAX_SHAPES, 1.0);
   h->pm.assign(SH_MAX_SHAPES * SH_MAX_SHAPES, 1.0);
   try {
-    h->scalars.ensure(16); h->bbox.ensure(8); h->counters.ensure(8);
+    h->scalars.ensure(16); h->bbox.ensure(8); h->counters.ensure(16);
   } catch (std::string &) { delete h; return -7; }
   cudaMemset(h->scalars.p, 0, 16 * sizeof(int));
-  cudaMemset(h->counters.p, 0, 8 * sizeof(unsigned long long));
+  cudaMemset(h->counters.p, 0, 16 * sizeof(unsigned long long));
   cudaMallocHost(&h->h_pinned, 64);
-  cudaEventCreate(&h->run_e0); cudaEventCreate(&h->run_e1);
-  h->ev.resize(2048);
+  cudaEventCreate(&h->run_e0); cudaEventCreate(&h->run_e1); cudaEventCreate(&h->ev_b0); cudaEventCreate(&h->ev_b1);
+  h->ev.resize(2048); h->ev2.resize(2048);
   for (auto &e : h->ev) cudaEventCreate(&e);
+  for (auto &e : h->ev2) cudaEventCreate(&e);
   *out = h;
   return 0;
 }
@@ -442,7 +548,7 @@ int sh_destroy(sh_ctx *h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  for (auto &d : h->shape_dev) { d.Ap.release(); d.ab.release(); d.node.release(); d.row_x.release(); d.cube.release(); }
+  for (auto &d : h->shape_dev) { d.Ap.release(); d.ab.release(); d.node.release(); d.row_x.release(); d.cube.release(); d.pf.release(); }
   h->d_shapes.release(); h->d_pk.release(); h->d_pm.release();
   DevBuf<double> *db[] = {&h->x, &h->v, &h->q, &h->L, &h->f, &h->tq, &h->c, &h->Rs, &h->c0, &h->wallf, &h->ewall, &h->ke, &h->bbox, &h->slot, &h->pres};
   for (auto *b : db) b->release();
@@ -451,6 +557,10 @@ int sh_destroy(sh_ctx *h) {
   for (auto *b : ib) b->release();
   h->counters.release();
   for (auto &e : h->ev) cudaEventDestroy(e);
+  for (auto &e : h->ev2) cudaEventDestroy(e);
+  h->pool.release(); h->pool_base.release(); h->pool_cap.release(); h->pd_off.release(); h->pool_count.release();
+  h->pd_cnt.release(); h->big_list.release(); h->split_flags.release();
+  if (h->h_pool_count) cudaFreeHost(h->h_pool_count);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   h->stage.release();
   cudaEventDestroy(h->run_e0); cudaEventDestroy(h->run_e1);
@@ -893,13 +1003,26 @@ int sh_get_timers(const sh_ctx *hc, double *seconds_pair, int64_t *pair_launches
   return 0;
 }
 
+int sh_get_split_stats(const sh_ctx *hc, double *seconds_eval, int64_t *eval_launches, int64_t *deep_pairs, int64_t *pool_redos) {
+  sh_ctx *h = const_cast<sh_ctx *>(hc);
+  CU(cudaSetDevice(h->device));
+  int rc = drain_events(h);
+  if (rc) return rc;
+  if (seconds_eval) *seconds_eval = h->sec_eval;
+  if (eval_launches) *eval_launches = h->eval_launches;
+  if (deep_pairs) *deep_pairs = h->big_pairs;
+  if (pool_redos) *pool_redos = h->split_redo;
+  return 0;
+}
+
 int sh_reset_timers(sh_ctx *h) {
   CU(cudaSetDevice(h->device));
   int rc = drain_events(h);
   if (rc) return rc;
   h->sec_pair = h->sec_neigh = h->sec_other = 0; h->pair_launches = 0; h->sec_run_total = 0;
+  h->sec_eval = 0; h->eval_launches = 0; h->big_pairs = 0; h->split_redo = 0;
   h->neighbor_builds = 0; h->kernel_launches = 0;
-  CU(cudaMemset(h->counters.p, 0, 8 * sizeof(unsigned long long)));
+  CU(cudaMemset(h->counters.p, 0, 16 * sizeof(unsigned long long)));
   return 0;
 }
 

@@ -151,9 +151,10 @@ def test_neighbor_skin_does_not_change_forces():
     assert np.abs(res[0] - res[1]).max() <= 1e-12 * np.abs(res[0]).max()
 
 
-@pytest.mark.parametrize("threads,variant", [(128, 1), (256, 1), (128, 0), (256, 0), (384, 0), (512, 0), (512, 2)])
+@pytest.mark.parametrize("threads,variant", [(128, 1), (256, 1), (128, 4), (256, 4), (384, 4), (512, 4), (512, 6), (0, 0), (0, 2)])
 def test_kernel_variants_agree_with_oracle(threads, variant):
-    """CTA-per-pair full-scan kernel (variant 1) and warp-per-pair windowed kernel (variant 0)."""
+    """variant bits: 1 = CTA-per-pair full-scan kernel; 4 = fused warp-per-pair kernel; 0 = split
+    cull/evaluate/reduce pipeline (default); 2 = direction-cell bound off."""
     cfg = W.config3_packing(256, lmax=20, grid=(32, 64))
     g, o = both(cfg)
     g.set_pair_tuning(threads, 0, variant)
@@ -161,9 +162,9 @@ def test_kernel_variants_agree_with_oracle(threads, variant):
     assert e["ncontact"] > 20
     if variant == 1:      # full scan: every counter equals the oracle's
         assert g.get_counters()["nodes_transformed"] == o.get_counters()["nodes_transformed"]
-    if variant in (1, 2):  # no direction-cell bound: every bounding-sphere survivor is evaluated, as in the oracle
+    if variant in (1, 2, 6):  # no direction-cell bound: every bounding-sphere survivor is evaluated, as in the oracle
         assert g.get_counters()["nodes_evaluated"] == o.get_counters()["nodes_evaluated"]
-    if variant == 0:
+    if variant in (0, 4):
         assert g.get_counters()["nodes_evaluated"] < o.get_counters()["nodes_evaluated"]
 
 
