@@ -240,6 +240,16 @@ class ShGpu:
         self._ck(self.L.sh_get_timers(self.h, C.byref(sp), C.byref(nl), C.byref(sn), C.byref(so)))
         return dict(seconds_pair=sp.value, pair_launches=nl.value, seconds_neigh=sn.value, seconds_other=so.value)
 
+    def get_counter_raw(self, index):
+        v = C.c_int64()
+        self._ck(self.L.sh_get_counter_raw(self.h, int(index), C.byref(v)))
+        return v.value
+
+    def get_split_times(self):
+        v = [C.c_double() for _ in range(4)]
+        self._ck(self.L.sh_get_split_times(self.h, *[C.byref(t) for t in v]))
+        return dict(zip(("cull", "eval", "reduce", "deep"), (t.value for t in v)))
+
     def get_split_stats(self):
         a, b, c, d = C.c_double(), C.c_int64(), C.c_int64(), C.c_int64()
         self._ck(self.L.sh_get_split_stats(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))

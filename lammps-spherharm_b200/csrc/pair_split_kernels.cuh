@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(WPB * 32) pair_eval_kernel(const DevShape *sha
     if (ra.flag != 2) { rec[ia].flag = rho < r ? 1 : 0; nev++; }
   }
   nev = __reduce_add_sync(0xffffffffu, nev);   // records preset by A (flag 2) are not "evaluated"
-  if (lane == 0 && nev) atomicAdd(&counters[2], (unsigned long long)nev);
+  if (lane == 0 && nev) { atomicAdd(&counters[2], (unsigned long long)nev); atomicAdd(&counters[5], (unsigned long long)nev); }
 }
 
 // ---- C: per-pair reduction + contact law.  One THREAD per pair: the two record runs are

@@ -87,7 +87,8 @@ struct sh_ctx {
   std::vector<long long> h_pool_cap;
   unsigned long long *h_pool_count = nullptr;  // pinned: [nshape] counts, then nbig, overflow
   cudaEvent_t ev_b0 = nullptr, ev_b1 = nullptr;
-  double sec_eval = 0, sec_cull = 0; int64_t eval_launches = 0;
+  double sec_eval = 0, sec_cull = 0, sec_reduce = 0, sec_deep = 0; int64_t eval_launches = 0;
+  std::vector<int> ev2_kind;
   int64_t big_pairs = 0, split_redo = 0;
   bool eval_pending = false;
   DevBuf<unsigned long long> counters;
@@ -308,7 +309,8 @@ int drain_events(sh_ctx *h) {
   for (size_t k = 0; k + 1 < h->ev2_used; k += 2) {
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev2[k], h->ev2[k + 1]);
-    h->sec_eval += ms * 1e-3;
+    double *dst[4] = {&h->sec_cull, &h->sec_eval, &h->sec_reduce, &h->sec_deep};
+    *dst[h->ev2_kind[k / 2] & 3] += ms * 1e-3;
   }
   h->ev2_used = 0;
   for (size_t k = 0; k + 1 < h->ev_used; k += 2) {
@@ -370,6 +372,13 @@ int run_split_pipeline(sh_ctx *h, PairArgs &P) {
   if ((int)h->h_pool_cap.size() != ns) {   // first sizing: 16 records per pair-direction, spread over the shapes
     h->h_pool_cap.assign(ns, std::max<long long>(4096, (long long)np * 32 / std::max(1, ns) * 2));
   }
+  auto tick = [&](int kind) -> int {   // start an event pair of the given class
+    if (h->ev2_used + 2 > h->ev2.size()) { if (drain_events(h)) return -2; }
+    h->ev2_kind[h->ev2_used / 2] = kind;
+    if (cudaEventRecord(h->ev2[h->ev2_used], h->stream) != cudaSuccess) return -2;
+    return 0;
+  };
+  auto tock = [&]() { cudaEventRecord(h->ev2[h->ev2_used + 1], h->stream); h->ev2_used += 2; };
   for (int attempt = 0; attempt < 6; attempt++) {
     std::vector<long long> base(ns);
     long long tot = 0;
@@ -383,7 +392,9 @@ int run_split_pipeline(sh_ctx *h, PairArgs &P) {
     S.pool = h->pool.p; S.pool_base = h->pool_base.p; S.pool_cap = h->pool_cap.p; S.pool_count = h->pool_count.p;
     S.pd_off = h->pd_off.p; S.pd_cnt = h->pd_cnt.p; S.big_list = h->big_list.p; S.nbig = h->split_flags.p; S.overflow = h->split_flags.p + 1;
     CU(cudaMemcpyAsync(h->counters.p + 8, h->counters.p, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, h->stream));
+    if (tick(0)) return -2;
     pair_cull_kernel<WPB><<<cdiv(np, WPB), WPB * 32, 0, h->stream>>>(P, S, (h->tune_variant & 2) ? 0 : 1);
+    tock();
     h->kernel_launches++;
     CU(cudaMemcpyAsync(h->h_pool_count, h->pool_count.p, ns * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(h->h_pool_count + SH_MAX_SHAPES, h->split_flags.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -411,23 +422,25 @@ int run_split_pipeline(sh_ctx *h, PairArgs &P) {
     if (nblk > 0) {
       const size_t smem = (size_t)maxT * 24 + 32;
       CU(cudaFuncSetAttribute(pair_eval_kernel<WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
-      if (h->ev2_used + 2 > h->ev2.size()) { if (drain_events(h)) return -2; }
-      CU(cudaEventRecord(h->ev2[h->ev2_used], h->stream));
+      if (tick(1)) return -2;
       pair_eval_kernel<WPB><<<nblk, WPB * 32, smem, h->stream>>>(h->d_shapes.p, S, plan, h->counters.p);
-      CU(cudaEventRecord(h->ev2[h->ev2_used + 1], h->stream));
-      h->ev2_used += 2;
+      tock();
       h->kernel_launches++; h->eval_launches++;
     }
     // ---- C
+    if (tick(2)) return -2;
     pair_reduce_kernel<<<cdiv(np, 128), 128, 0, h->stream>>>(P, S);
+    tock();
     h->kernel_launches++;
     // ---- deep contacts
     if (nbig > 0) {
       PairArgs Pb = P;
       Pb.pair_list = h->big_list.p; Pb.npairs = nbig;
       CU(cudaMemsetAsync(h->scalars.p + 2, 0, sizeof(int), h->stream));
+      if (tick(3)) return -2;
       int rc = launch_fused(h, Pb);
       if (rc) return rc;
+      tock();
       h->kernel_launches++;
       h->big_pairs += nbig;
     }
@@ -537,7 +550,7 @@ int sh_create(sh_ctx **out, int device_id) {
   cudaMemset(h->counters.p, 0, 16 * sizeof(unsigned long long));
   cudaMallocHost(&h->h_pinned, 64);
   cudaEventCreate(&h->run_e0); cudaEventCreate(&h->run_e1); cudaEventCreate(&h->ev_b0); cudaEventCreate(&h->ev_b1);
-  h->ev.resize(2048); h->ev2.resize(2048);
+  h->ev.resize(2048); h->ev2.resize(4096); h->ev2_kind.resize(2048);
   for (auto &e : h->ev) cudaEventCreate(&e);
   for (auto &e : h->ev2) cudaEventCreate(&e);
   *out = h;
@@ -1003,6 +1016,29 @@ int sh_get_timers(const sh_ctx *hc, double *seconds_pair, int64_t *pair_launches
   return 0;
 }
 
+int sh_get_counter_raw(const sh_ctx *hc, int index, int64_t *value) {
+  sh_ctx *h = const_cast<sh_ctx *>(hc);
+  if (index < 0 || index >= 8) return fail(h, "counter index out of range");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  unsigned long long c = 0;
+  CU(cudaMemcpy(&c, h->counters.p + index, sizeof c, cudaMemcpyDeviceToHost));
+  if (value) *value = (int64_t)c;
+  return 0;
+}
+
+int sh_get_split_times(const sh_ctx *hc, double *seconds_cull, double *seconds_eval, double *seconds_reduce, double *seconds_deep) {
+  sh_ctx *h = const_cast<sh_ctx *>(hc);
+  CU(cudaSetDevice(h->device));
+  int rc = drain_events(h);
+  if (rc) return rc;
+  if (seconds_cull) *seconds_cull = h->sec_cull;
+  if (seconds_eval) *seconds_eval = h->sec_eval;
+  if (seconds_reduce) *seconds_reduce = h->sec_reduce;
+  if (seconds_deep) *seconds_deep = h->sec_deep;
+  return 0;
+}
+
 int sh_get_split_stats(const sh_ctx *hc, double *seconds_eval, int64_t *eval_launches, int64_t *deep_pairs, int64_t *pool_redos) {
   sh_ctx *h = const_cast<sh_ctx *>(hc);
   CU(cudaSetDevice(h->device));
@@ -1020,7 +1056,7 @@ int sh_reset_timers(sh_ctx *h) {
   int rc = drain_events(h);
   if (rc) return rc;
   h->sec_pair = h->sec_neigh = h->sec_other = 0; h->pair_launches = 0; h->sec_run_total = 0;
-  h->sec_eval = 0; h->eval_launches = 0; h->big_pairs = 0; h->split_redo = 0;
+  h->sec_eval = h->sec_cull = h->sec_reduce = h->sec_deep = 0; h->eval_launches = 0; h->big_pairs = 0; h->split_redo = 0;
   h->neighbor_builds = 0; h->kernel_launches = 0;
   CU(cudaMemset(h->counters.p, 0, 16 * sizeof(unsigned long long)));
   return 0;
