@@ -27,6 +27,8 @@ struct DevShape {
   const float *cube_b2;                   // conservative r^2 upper bound per cube-map direction cell (6*cube_n^2)
   int cube_n, pad2_;
   const float *pf;                        // FP32 copy of the node points (3 x nq, SoA) for the conservative pre-cull
+  const float *cube_w2;                   // candidate-cache table (inflated wide bound^2 per direction cell)
+  double cache_delta;                     // node displacement margin of the candidate cache
 };
 
 // rotation matrix (row-major R[3*r+c]) of unit quaternion (w,x,y,z); plain mul/add, fixed order

@@ -40,8 +40,203 @@ struct SplitArgs {
   int *overflow;
 };
 
+// ---- conservative window on a's node grid (FP32 with margins), shared by the cull and cache-build kernels.
+// Rb = radius of the sphere around b's origin that a node must enter (rmax_b, or rmax_b + delta for the cache).
+struct NodeWindow { bool skip; float cosA, xe, se, phie; };
+
+__device__ __forceinline__ NodeWindow make_window(const DevShape &sa, double Rb, const double *x0) {
+  NodeWindow w;
+  const double e0 = 2.0 * x0[0], e1 = 2.0 * x0[1], e2 = 2.0 * x0[2];   // b's origin in a's frame
+  const double D2 = e0 * e0 + e1 * e1 + e2 * e2, D = sqrt(D2);
+  w.skip = D >= (sa.rmax + Rb) * (1.0 + 1e-9);
+  w.cosA = -2.0f; w.xe = 1.0f; w.se = 0.0f; w.phie = 0.0f;
+  if (!w.skip && D > 1e-9) {
+    const double q = D2 - Rb * Rb;
+    double rc = sa.rmin;
+    if (q > 0) rc = fmin(fmax(sqrt(q), sa.rmin), sa.rmax);
+    const double g = (rc * rc + q) / (2.0 * rc * D);
+    w.cosA = (float)g - 3e-5f;
+    if (w.cosA >= 1.0f) w.skip = true;
+    w.xe = fminf(1.0f, fmaxf(-1.0f, (float)(e2 / D)));
+    w.se = sqrtf(fmaxf(0.0f, 1.0f - w.xe * w.xe));
+    w.phie = atan2f((float)e1, (float)e0);
+    if (w.phie < 0.0f) w.phie += 6.2831853f;
+  }
+  return w;
+}
+
+__device__ __forceinline__ void classify_row(const DevShape &sa, const NodeWindow &w, int row, int &c0, int &ccount) {
+  c0 = 0; ccount = 0;
+  const int nph = sa.n_phi;
+  if (row >= sa.n_theta) return;
+  if (w.cosA <= -1.0f) { ccount = nph; return; }
+  const float xa = sa.row_x[row];
+  const float sarow = sqrtf(fmaxf(0.0f, 1.0f - xa * xa));
+  const float ss = sarow * w.se, xx = xa * w.xe;
+  if (xx + ss < w.cosA) return;
+  const float cd = (ss > 1e-12f) ? (w.cosA - xx) / ss : -2.0f;
+  if (cd <= -1.0f) { ccount = nph; return; }
+  const float inv_dphi = (float)nph * 0.15915494f;
+  const float dl = acosf(fminf(cd, 1.0f)) + 2e-4f;
+  const int b0 = (int)ceilf((w.phie - dl) * inv_dphi - 0.5f);
+  const int b1 = (int)floorf((w.phie + dl) * inv_dphi - 0.5f);
+  ccount = b1 - b0 + 1;
+  if (ccount >= nph) { ccount = nph; c0 = 0; }
+  else if (ccount > 0) { c0 = b0 % nph; if (c0 < 0) c0 += nph; }
+  else ccount = 0;
+}
+
+// cube-map direction cell of a vector (FP32); the tables are conservative across cell borders
+__device__ __forceinline__ int cube_cell(float f0, float f1, float f2, int cn) {
+  const float ax = fabsf(f0), ay = fabsf(f1), az = fabsf(f2);
+  int face; float ma, uu, vv;
+  if (ax >= ay && ax >= az) { face = f0 > 0 ? 0 : 1; ma = ax; uu = f1; vv = f2; }
+  else if (ay >= az) { face = f1 > 0 ? 2 : 3; ma = ay; uu = f0; vv = f2; }
+  else { face = f2 > 0 ? 4 : 5; ma = az; uu = f0; vv = f1; }
+  const float im = 1.0f / fmaxf(ma, 1e-30f), hn = 0.5f * (float)cn;
+  const int iu = min(cn - 1, max(0, (int)((uu * im + 1.0f) * hn)));
+  const int iv = min(cn - 1, max(0, (int)((vv * im + 1.0f) * hn)));
+  return (face * cn + iu) * cn + iv;
+}
+
+// relative pose of direction a -> b into the warp's shared scratch: M[9], t[3], x0[3] (same fma chains as the oracle)
+__device__ __forceinline__ void pose_to_smem(const PairArgs &A, int a, int b, double dd0, double dd1, double dd2, int lane,
+                                             double *pose) {
+  const int st = A.stride;
+  __syncwarp();
+  if (lane < 15) {
+    double val;
+    if (lane < 9) {
+      const int r = lane / 3, k = lane - 3 * r;
+      double m = A.Rs[(0 + r) * st + b] * A.Rs[(0 + k) * st + a];
+      m = fma(A.Rs[(3 + r) * st + b], A.Rs[(3 + k) * st + a], m);
+      m = fma(A.Rs[(6 + r) * st + b], A.Rs[(6 + k) * st + a], m);
+      val = m;
+    } else if (lane < 12) {
+      const int r = lane - 9;
+      double tt = A.Rs[(0 + r) * st + b] * dd0;
+      tt = fma(A.Rs[(3 + r) * st + b], dd1, tt);
+      tt = fma(A.Rs[(6 + r) * st + b], dd2, tt);
+      val = tt;
+    } else {
+      const int r = lane - 12;
+      double hx = A.Rs[(0 + r) * st + a] * dd0;
+      hx = fma(A.Rs[(3 + r) * st + a], dd1, hx);
+      hx = fma(A.Rs[(6 + r) * st + a], dd2, hx);
+      val = -0.5 * hx;
+    }
+    pose[lane] = val;
+  }
+  __syncwarp();
+}
+
+#define CACHE_CAP 256
+
+struct CacheArgs {
+  unsigned short *pool;            // candidate node indices of all (pair, direction) runs
+  long long *off;                  // [2P]
+  int *cnt;                        // [2P]  -1 = not cached (too many candidates): the cull falls back to the window
+  unsigned long long *count;       // appended entries (may exceed cap -> host grows and rebuilds)
+  long long cap;
+  int *overflow;
+  const int *invalid;              // device flag raised by cache_check_kernel: the cull ignores the cache when set
+  int enabled;
+};
+
+// ---- candidate cache build (on neighbor rebuilds and when a particle has used up its displacement margin):
+// window + FP32 tests against the INFLATED bounds (rmax_b + delta; cube_w2), no FP64 work.
 template <int WPB>
-__global__ void __launch_bounds__(WPB * 32, 3) pair_cull_kernel(PairArgs A, SplitArgs S, int use_bounds) {
+__global__ void __launch_bounds__(WPB * 32, 4) pair_cache_build_kernel(PairArgs A, CacheArgs C) {
+  __shared__ unsigned short s_buf[WPB][CACHE_CAP];
+  __shared__ double s_pose[WPB][16];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int p = blockIdx.x * WPB + warp;
+  if (p >= A.npairs) return;
+  const int st = A.stride;
+  const int i = A.pair_i[p], j = A.pair_j[p];
+  double d[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    double dk = A.c[k * st + i] - A.c[k * st + j];
+    if (A.periodic[k]) dk = dk - A.boxlen[k] * rint(dk / A.boxlen[k]);
+    d[k] = dk;
+  }
+  const int shp_i = A.shape[i], shp_j = A.shape[j];
+  double *pose = s_pose[warp];
+  unsigned short *buf = s_buf[warp];
+  for (int dir = 0; dir < 2; dir++) {
+    const int a = dir ? j : i, b = dir ? i : j;
+    const DevShape &sa = A.shapes[dir ? shp_j : shp_i];
+    const DevShape &sb = A.shapes[dir ? shp_i : shp_j];
+    const double sgn = dir ? -1.0 : 1.0;
+    pose_to_smem(A, a, b, sgn * d[0], sgn * d[1], sgn * d[2], lane, pose);
+    const double *M = pose, *t = pose + 9, *x0 = pose + 12;
+    const double delta = sb.cache_delta, Rb = sb.rmax + delta;
+    const NodeWindow w = make_window(sa, Rb, x0);
+    const float *__restrict__ pf = sa.pf;
+    const float *__restrict__ cube = sb.cube_w2;
+    const int cn = sb.cube_n, nq = sa.nq, nph = sa.n_phi, nth = sa.n_theta;
+    const float fM0 = (float)M[0], fM1 = (float)M[1], fM2 = (float)M[2], fM3 = (float)M[3], fM4 = (float)M[4],
+                fM5 = (float)M[5], fM6 = (float)M[6], fM7 = (float)M[7], fM8 = (float)M[8];
+    const float ft0 = (float)t[0], ft1 = (float)t[1], ft2 = (float)t[2];
+    const float fR2 = (float)(Rb * Rb) + 1e-4f;
+    const float fin = (float)((sb.rmin + 2.0 * delta) * (sb.rmin + 2.0 * delta)) + 1e-4f;
+    int n = 0;
+    bool over = false;
+    if (!w.skip) {
+      for (int rb = 0; rb < nth && !over; rb += 32) {
+        int c0, ccount;
+        classify_row(sa, w, rb + lane, c0, ccount);
+        unsigned rows = __ballot_sync(0xffffffffu, ccount > 0);
+        while (rows && !over) {
+          const int rl = __ffs(rows) - 1;
+          rows &= rows - 1;
+          const int rc0 = __shfl_sync(0xffffffffu, c0, rl), rcount = __shfl_sync(0xffffffffu, ccount, rl);
+          const int rowbase = (rb + rl) * nph;
+          for (int cb = 0; cb < rcount; cb += 32) {
+            const int cc = cb + lane;
+            bool pass = false;
+            int k = 0;
+            if (cc < rcount) {
+              int col = rc0 + cc;
+              if (col >= nph) col -= nph;
+              k = rowbase + col;
+              const float q0 = pf[k], q1 = pf[nq + k], q2 = pf[2 * nq + k];
+              const float f0 = fmaf(fM2, q2, fmaf(fM1, q1, fmaf(fM0, q0, ft0)));
+              const float f1 = fmaf(fM5, q2, fmaf(fM4, q1, fmaf(fM3, q0, ft1)));
+              const float f2 = fmaf(fM8, q2, fmaf(fM7, q1, fmaf(fM6, q0, ft2)));
+              const float r2 = fmaf(f2, f2, fmaf(f1, f1, f0 * f0));
+              if (r2 < fR2) pass = (r2 < fin) || (r2 < __ldg(&cube[cube_cell(f0, f1, f2, cn)]) + 1e-4f);
+            }
+            const unsigned pm = __ballot_sync(0xffffffffu, pass);
+            if (pm) {
+              const int nnew = __popc(pm);
+              if (n + nnew > CACHE_CAP) { over = true; break; }
+              if (pass) buf[n + __popc(pm & ((1u << lane) - 1u))] = (unsigned short)k;
+              n += nnew;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    long long off = 0;
+    if (over) n = -1;
+    if (lane == 0 && n > 0) off = (long long)atomicAdd(C.count, (unsigned long long)n);
+    off = __shfl_sync(0xffffffffu, off, 0);
+    if (n > 0) {
+      if (off + n <= C.cap) { for (int r = lane; r < n; r += 32) C.pool[off + r] = buf[r]; }
+      else { if (lane == 0) *C.overflow = 1; n = -1; }
+    }
+    if (lane == 0) { C.off[2 * p + dir] = off; C.cnt[2 * p + dir] = n; }
+    __syncwarp();
+  }
+}
+
+// ---- A: cull.  Per (pair, direction): candidates (from the cache, else from the window + FP32 pre-cull) ->
+// exact FP64 stage on full warps -> survivor records -> one contiguous run in the target shape's pool.
+template <int WPB>
+__global__ void __launch_bounds__(WPB * 32, 3) pair_cull_kernel(PairArgs A, SplitArgs S, CacheArgs C, int use_bounds) {
   __shared__ __align__(16) SurvRec s_rec[WPB][2][SPLIT_CAP];
   __shared__ double s_pose[WPB][16];
   __shared__ unsigned short s_cand[WPB][64];
@@ -62,38 +257,20 @@ __global__ void __launch_bounds__(WPB * 32, 3) pair_cull_kernel(PairArgs A, Spli
   int cnt[2] = {0, 0};
   bool big = false;
   unsigned long long n_trans = 0;
+  bool cached = false;
+  int ccnt[2] = {0, 0};
+  if (C.enabled && *C.invalid == 0) {
+    ccnt[0] = C.cnt[2 * p]; ccnt[1] = C.cnt[2 * p + 1];
+    cached = ccnt[0] >= 0 && ccnt[1] >= 0;
+  }
 
   for (int dir = 0; dir < 2 && !big; dir++) {
     const int a = dir ? j : i, b = dir ? i : j;
     const DevShape &sa = A.shapes[dir ? shp_j : shp_i];
     const DevShape &sb = A.shapes[dir ? shp_i : shp_j];
     const double sgn = dir ? -1.0 : 1.0;
-    const double dd0 = sgn * d[0], dd1 = sgn * d[1], dd2 = sgn * d[2];
-    __syncwarp();
-    if (lane < 15) {
-      double val;
-      if (lane < 9) {
-        const int r = lane / 3, k = lane - 3 * r;
-        double m = A.Rs[(0 + r) * st + b] * A.Rs[(0 + k) * st + a];
-        m = fma(A.Rs[(3 + r) * st + b], A.Rs[(3 + k) * st + a], m);
-        m = fma(A.Rs[(6 + r) * st + b], A.Rs[(6 + k) * st + a], m);
-        val = m;
-      } else if (lane < 12) {
-        const int r = lane - 9;
-        double tt = A.Rs[(0 + r) * st + b] * dd0;
-        tt = fma(A.Rs[(3 + r) * st + b], dd1, tt);
-        tt = fma(A.Rs[(6 + r) * st + b], dd2, tt);
-        val = tt;
-      } else {
-        const int r = lane - 12;
-        double hx = A.Rs[(0 + r) * st + a] * dd0;
-        hx = fma(A.Rs[(3 + r) * st + a], dd1, hx);
-        hx = fma(A.Rs[(6 + r) * st + a], dd2, hx);
-        val = -0.5 * hx;
-      }
-      pose[lane] = val;
-    }
-    __syncwarp();
+    if (cached && ccnt[dir] == 0) { cnt[dir] = 0; continue; }
+    pose_to_smem(A, a, b, sgn * d[0], sgn * d[1], sgn * d[2], lane, pose);
     const double *M = pose, *t = pose + 9, *x0 = pose + 12;
     const double rmax2 = sb.rmax2, rmin2 = sb.rmin2;
     const double *__restrict__ nodes = sa.px;
@@ -102,20 +279,13 @@ __global__ void __launch_bounds__(WPB * 32, 3) pair_cull_kernel(PairArgs A, Spli
     const int cn = sb.cube_n;
     SurvRec *buf = s_rec[warp][dir];
     unsigned short *cand = s_cand[warp];
-    int queued = 0, ncand = 0;
-    // FP32 copies for the conservative pre-cull (absolute margin 1e-4 on rho^2 >> FP32 rounding of s)
-    const float *__restrict__ pf = sa.pf;
-    const float fM0 = (float)M[0], fM1 = (float)M[1], fM2 = (float)M[2], fM3 = (float)M[3], fM4 = (float)M[4],
-                fM5 = (float)M[5], fM6 = (float)M[6], fM7 = (float)M[7], fM8 = (float)M[8];
-    const float ft0 = (float)t[0], ft1 = (float)t[1], ft2 = (float)t[2];
-    const float frmax2 = (float)rmax2 + 1e-4f;
+    int queued = 0;
 
-    // exact FP64 stage on candidates cand[0..m): transform, bounding sphere, inscribed sphere, direction-cell bound
-    auto exact_stage = [&](int m) {
-      int flag = -1, k = 0;
+    // exact FP64 stage: transform, bounding sphere, inscribed sphere, direction-cell bound
+    auto exact_stage = [&](bool valid, int k) {
+      int flag = -1;
       double s0 = 0, s1 = 0, s2 = 0;
-      if (lane < m) {
-        k = cand[lane];
+      if (valid) {
         const double p0 = nodes[k], p1 = nodes[nq + k], p2 = nodes[2 * nq + k];
         s0 = fma(M[0], p0, t[0]); s0 = fma(M[1], p1, s0); s0 = fma(M[2], p2, s0);
         s1 = fma(M[3], p0, t[1]); s1 = fma(M[4], p1, s1); s1 = fma(M[5], p2, s1);
@@ -123,18 +293,8 @@ __global__ void __launch_bounds__(WPB * 32, 3) pair_cull_kernel(PairArgs A, Spli
         const double rho2 = fma(s2, s2, fma(s1, s1, s0 * s0));
         if (rho2 < rmax2) {
           if (rho2 <= rmin2) flag = 2;
-          else if (use_bounds) {
-            const float fx = (float)s0, fy = (float)s1, fz = (float)s2;
-            const float ax = fabsf(fx), ay = fabsf(fy), az = fabsf(fz);
-            int face; float ma, uu, vv;
-            if (ax >= ay && ax >= az) { face = fx > 0 ? 0 : 1; ma = ax; uu = fy; vv = fz; }
-            else if (ay >= az) { face = fy > 0 ? 2 : 3; ma = ay; uu = fx; vv = fz; }
-            else { face = fz > 0 ? 4 : 5; ma = az; uu = fx; vv = fy; }
-            const float im = 1.0f / ma, hn = 0.5f * (float)cn;
-            const int iu = min(cn - 1, max(0, (int)((uu * im + 1.0f) * hn)));
-            const int iv = min(cn - 1, max(0, (int)((vv * im + 1.0f) * hn)));
-            if (rho2 < (double)__ldg(&cube[(face * cn + iu) * cn + iv])) flag = 0;
-          } else flag = 0;
+          else if (use_bounds) { if (rho2 < (double)__ldg(&cube[cube_cell((float)s0, (float)s1, (float)s2, cn)])) flag = 0; }
+          else flag = 0;
         }
       }
       const unsigned sm = __ballot_sync(0xffffffffu, flag >= 0);
@@ -149,107 +309,71 @@ __global__ void __launch_bounds__(WPB * 32, 3) pair_cull_kernel(PairArgs A, Spli
       }
     };
 
-    // conservative window (identical to pair_warp_kernel.cuh)
-    const double e0 = 2.0 * x0[0], e1 = 2.0 * x0[1], e2 = 2.0 * x0[2];
-    const double D2 = e0 * e0 + e1 * e1 + e2 * e2, D = sqrt(D2);
-    bool skip = D >= (sa.rmax + sb.rmax) * (1.0 + 1e-9);
-    float cosA = -2.0f, xe = 1.0f, se = 0.0f, phie = 0.0f;
-    if (!skip && D > 1e-9) {
-      const double q = D2 - rmax2;
-      double rc = sa.rmin;
-      if (q > 0) rc = fmin(fmax(sqrt(q), sa.rmin), sa.rmax);
-      const double g = (rc * rc + q) / (2.0 * rc * D);
-      cosA = (float)g - 3e-5f;
-      if (cosA >= 1.0f) skip = true;
-      xe = (float)(e2 / D);
-      xe = fminf(1.0f, fmaxf(-1.0f, xe));
-      se = sqrtf(fmaxf(0.0f, 1.0f - xe * xe));
-      phie = atan2f((float)e1, (float)e0);
-      if (phie < 0.0f) phie += 6.2831853f;
-    }
-    if (!skip) {
-      const int nth = sa.n_theta, nph = sa.n_phi;
-      const float inv_dphi = (float)nph * 0.15915494f;
-      for (int rb = 0; rb < nth && !big; rb += 32) {
-        const int row = rb + lane;
-        int c0 = 0, ccount = 0;
-        if (row < nth) {
-          if (cosA <= -1.0f) { ccount = nph; }
-          else {
-            const float xa = sa.row_x[row];
-            const float sarow = sqrtf(fmaxf(0.0f, 1.0f - xa * xa));
-            const float ss = sarow * se, xx = xa * xe;
-            if (xx + ss >= cosA) {
-              float cd = (ss > 1e-12f) ? (cosA - xx) / ss : -2.0f;
-              if (cd <= -1.0f) ccount = nph;
-              else {
-                const float dl = acosf(fminf(cd, 1.0f)) + 2e-4f;
-                const int b0 = (int)ceilf((phie - dl) * inv_dphi - 0.5f);
-                const int b1 = (int)floorf((phie + dl) * inv_dphi - 0.5f);
-                ccount = b1 - b0 + 1;
-                if (ccount >= nph) { ccount = nph; c0 = 0; }
-                else if (ccount > 0) { c0 = b0 % nph; if (c0 < 0) c0 += nph; }
-                else ccount = 0;
+    if (cached) {
+      const unsigned short *__restrict__ cl = C.pool + C.off[2 * p + dir];
+      const int m = ccnt[dir];
+      for (int g = 0; g < m && !big; g += 32) {
+        const bool valid = g + lane < m;
+        exact_stage(valid, valid ? (int)cl[g + lane] : 0);
+      }
+      n_trans += m;
+    } else {
+      const NodeWindow w = make_window(sa, sb.rmax, x0);
+      if (!w.skip) {
+        const float *__restrict__ pf = sa.pf;
+        const float fM0 = (float)M[0], fM1 = (float)M[1], fM2 = (float)M[2], fM3 = (float)M[3], fM4 = (float)M[4],
+                    fM5 = (float)M[5], fM6 = (float)M[6], fM7 = (float)M[7], fM8 = (float)M[8];
+        const float ft0 = (float)t[0], ft1 = (float)t[1], ft2 = (float)t[2];
+        const float frmax2 = (float)rmax2 + 1e-4f;
+        const int nth = sa.n_theta, nph = sa.n_phi;
+        int ncand = 0;
+        for (int rb = 0; rb < nth && !big; rb += 32) {
+          int c0, ccount;
+          classify_row(sa, w, rb + lane, c0, ccount);
+          unsigned rows = __ballot_sync(0xffffffffu, ccount > 0);
+          while (rows && !big) {
+            const int rl = __ffs(rows) - 1;
+            rows &= rows - 1;
+            const int rc0 = __shfl_sync(0xffffffffu, c0, rl), rcount = __shfl_sync(0xffffffffu, ccount, rl);
+            const int rowbase = (rb + rl) * nph;
+            for (int cb = 0; cb < rcount && !big; cb += 32) {
+              const int cc = cb + lane;
+              bool pass = false;
+              int k = 0;
+              if (cc < rcount) {
+                int col = rc0 + cc;
+                if (col >= nph) col -= nph;
+                k = rowbase + col;
+                const float q0 = pf[k], q1 = pf[nq + k], q2 = pf[2 * nq + k];
+                const float f0 = fmaf(fM2, q2, fmaf(fM1, q1, fmaf(fM0, q0, ft0)));
+                const float f1 = fmaf(fM5, q2, fmaf(fM4, q1, fmaf(fM3, q0, ft1)));
+                const float f2 = fmaf(fM8, q2, fmaf(fM7, q1, fmaf(fM6, q0, ft2)));
+                const float r2 = fmaf(f2, f2, fmaf(f1, f1, f0 * f0));
+                if (r2 < frmax2) pass = !use_bounds || r2 < __ldg(&cube[cube_cell(f0, f1, f2, cn)]) + 1e-4f;
               }
-            }
-          }
-        }
-        unsigned rows = __ballot_sync(0xffffffffu, ccount > 0);
-        while (rows && !big) {
-          const int rl = __ffs(rows) - 1;
-          rows &= rows - 1;
-          const int rc0 = __shfl_sync(0xffffffffu, c0, rl), rcount = __shfl_sync(0xffffffffu, ccount, rl);
-          const int rowbase = (rb + rl) * nph;
-          for (int cb = 0; cb < rcount && !big; cb += 32) {
-            const int cc = cb + lane;
-            bool pass = false;
-            int k = 0;
-            if (cc < rcount) {
-              int col = rc0 + cc;
-              if (col >= nph) col -= nph;
-              k = rowbase + col;
-              const float q0 = pf[k], q1 = pf[nq + k], q2 = pf[2 * nq + k];
-              const float f0 = fmaf(fM2, q2, fmaf(fM1, q1, fmaf(fM0, q0, ft0)));
-              const float f1 = fmaf(fM5, q2, fmaf(fM4, q1, fmaf(fM3, q0, ft1)));
-              const float f2 = fmaf(fM8, q2, fmaf(fM7, q1, fmaf(fM6, q0, ft2)));
-              const float r2 = fmaf(f2, f2, fmaf(f1, f1, f0 * f0));
-              if (r2 < frmax2) {
-                pass = true;
-                if (use_bounds) {
-                  const float ax = fabsf(f0), ay = fabsf(f1), az = fabsf(f2);
-                  int face; float ma, uu, vv;
-                  if (ax >= ay && ax >= az) { face = f0 > 0 ? 0 : 1; ma = ax; uu = f1; vv = f2; }
-                  else if (ay >= az) { face = f1 > 0 ? 2 : 3; ma = ay; uu = f0; vv = f2; }
-                  else { face = f2 > 0 ? 4 : 5; ma = az; uu = f0; vv = f1; }
-                  const float im = 1.0f / fmaxf(ma, 1e-30f), hn = 0.5f * (float)cn;
-                  const int iu = min(cn - 1, max(0, (int)((uu * im + 1.0f) * hn)));
-                  const int iv = min(cn - 1, max(0, (int)((vv * im + 1.0f) * hn)));
-                  pass = r2 < __ldg(&cube[(face * cn + iu) * cn + iv]) + 1e-4f;
+              n_trans += min(32, rcount - cb);
+              const unsigned pm = __ballot_sync(0xffffffffu, pass);
+              if (pm) {
+                if (pass) cand[ncand + __popc(pm & ((1u << lane) - 1u))] = (unsigned short)k;
+                ncand += __popc(pm);
+                __syncwarp();
+                if (ncand >= 32) {
+                  exact_stage(true, (int)cand[lane]);
+                  __syncwarp();
+                  const int rem = ncand - 32;
+                  unsigned short mv = 0;
+                  if (lane < rem) mv = cand[32 + lane];
+                  __syncwarp();
+                  if (lane < rem) cand[lane] = mv;
+                  ncand = rem;
+                  __syncwarp();
                 }
               }
             }
-            n_trans += min(32, rcount - cb);
-            const unsigned pm = __ballot_sync(0xffffffffu, pass);
-            if (pm) {
-              if (pass) cand[ncand + __popc(pm & ((1u << lane) - 1u))] = (unsigned short)k;
-              ncand += __popc(pm);
-              __syncwarp();
-              if (ncand >= 32) {
-                exact_stage(32);
-                __syncwarp();
-                const int rem = ncand - 32;
-                unsigned short mv = 0;
-                if (lane < rem) mv = cand[32 + lane];
-                __syncwarp();
-                if (lane < rem) cand[lane] = mv;
-                ncand = rem;
-                __syncwarp();
-              }
-            }
           }
         }
+        if (!big && ncand > 0) { exact_stage(lane < ncand, lane < ncand ? (int)cand[lane] : 0); __syncwarp(); }
       }
-      if (!big && ncand > 0) { exact_stage(ncand); __syncwarp(); }
     }
     cnt[dir] = queued;
   }

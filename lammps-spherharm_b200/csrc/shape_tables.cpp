@@ -203,6 +203,59 @@ void build_cube_bounds(ShapeTables &s, int n, int sub) {
   }
 }
 
+// Table for the candidate cache (pair_split_kernels.cuh).  A node cached at build time with direction d0 (as
+// seen from this shape's centre) and radius rho0 may move by at most delta before the cache is rebuilt, so its
+// direction drifts by at most gamma = asin(delta / (rmin + 2 delta)) (nodes closer than rmin + 2 delta are cached
+// unconditionally).  wide2(cell) = (sqrt(max cube_bound2 over all cells within gamma of the cell) + delta)^2.
+void build_cache_table(ShapeTables &s) {
+  const int n = s.cube_n;
+  s.cache_delta = 0.02 * s.rmax;
+  const double ratio = s.cache_delta / (s.rmin + 2.0 * s.cache_delta);
+  const double gamma = 1.1 * std::asin(std::min(1.0, ratio)) + 1e-3;
+  std::vector<double> dir((size_t)6 * n * n * 3), hd((size_t)6 * n * n);
+  auto cell_dir = [&](int f, double u, double v, double *d) {
+    const int major = f / 2;
+    d[major] = (f % 2) ? -1.0 : 1.0;
+    d[major == 0 ? 1 : 0] = u;
+    d[major == 2 ? 1 : 2] = v;
+    const double nn = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    for (int k = 0; k < 3; k++) d[k] /= nn;
+  };
+  const double du = 2.0 / n, ov = du / 6.0;   // cells cover their own extent plus the one-sub-step overlap
+  for (int f = 0; f < 6; f++)
+    for (int iu = 0; iu < n; iu++)
+      for (int iv = 0; iv < n; iv++) {
+        const size_t c = ((size_t)f * n + iu) * n + iv;
+        const double u0 = -1.0 + iu * du, v0 = -1.0 + iv * du;
+        cell_dir(f, u0 + 0.5 * du, v0 + 0.5 * du, &dir[3 * c]);
+        double worst = 0;
+        for (int a = 0; a < 2; a++)
+          for (int b = 0; b < 2; b++) {
+            double cd[3];
+            cell_dir(f, u0 - ov + a * (du + 2 * ov), v0 - ov + b * (du + 2 * ov), cd);
+            const double dot = cd[0] * dir[3 * c] + cd[1] * dir[3 * c + 1] + cd[2] * dir[3 * c + 2];
+            worst = std::max(worst, std::acos(std::min(1.0, std::max(-1.0, dot))));
+          }
+        hd[c] = worst;   // angular half-diagonal of the (overlapped) cell
+      }
+  const size_t nc = (size_t)6 * n * n;
+  s.cube_wide2.assign(nc, 0.0f);
+  double hdmax = 0;
+  for (size_t c = 0; c < nc; c++) hdmax = std::max(hdmax, hd[c]);
+  const double reach = gamma + 2.0 * hdmax + 1e-6;
+  const double cos_reach = reach >= 3.14159 ? -2.0 : std::cos(reach);
+  for (size_t c = 0; c < nc; c++) {
+    float mx = 0.0f;
+    for (size_t e = 0; e < nc; e++) {
+      const double dot = dir[3 * c] * dir[3 * e] + dir[3 * c + 1] * dir[3 * e + 1] + dir[3 * c + 2] * dir[3 * e + 2];
+      if (dot >= cos_reach) mx = std::max(mx, s.cube_bound2[e]);
+    }
+    const double w = std::sqrt((double)mx) + s.cache_delta;
+    float w2 = (float)(w * w * (1.0 + 1e-6));
+    s.cube_wide2[c] = std::nextafter(w2, 3.0e38f);
+  }
+}
+
 // cyclic Jacobi for a symmetric 3x3 (principal inertia axes)
 void jacobi_sym3(double A[3][3], double ev[3], double V[3][3]) {
   for (int i = 0; i < 3; i++)
@@ -339,6 +392,7 @@ std::string build_shape_tables(int lmax, const double *a_lm, const double *b_lm,
   for (int d = 0; d < 4; d++) s.quat_principal[d] = qp[d];
   rotation_from_quat(qp, s.Rp);
   build_cube_bounds(s, 24, 6);
+  build_cache_table(s);
   return "";
 }
 

@@ -25,6 +25,10 @@ struct ShapeTables {
   // a node with rho^2 >= bound2(cell(direction)) is certainly outside, no SH evaluation needed
   int cube_n = 0;
   std::vector<float> cube_bound2;
+  // candidate-cache table: (sqrt(max of cube_bound2 over all cells within the angle a node direction can drift
+  // before the cache is rebuilt) + cache_delta)^2; cache_delta = node displacement margin of the cache
+  std::vector<float> cube_wide2;
+  double cache_delta = 0;
   std::vector<double> row_x;             // cos(theta) of the Gauss-Legendre rows (node k = row*n_phi+col)
   double density = 1, volume = 0, mass = 0;
   std::array<double, 3> com{}, inertia{};

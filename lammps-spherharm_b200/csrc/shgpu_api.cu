@@ -42,7 +42,7 @@ struct DevBuf {
 struct ShapeDev {
   DevBuf<double> Ap, node;   // node: 6 x nq
   DevBuf<double2> ab;
-  DevBuf<float> row_x, cube, pf;
+  DevBuf<float> row_x, cube, pf, cubew;
 };
 
 }  // namespace
@@ -89,7 +89,15 @@ struct sh_ctx {
   cudaEvent_t ev_b0 = nullptr, ev_b1 = nullptr;
   double sec_eval = 0, sec_cull = 0, sec_reduce = 0, sec_deep = 0; int64_t eval_launches = 0;
   std::vector<int> ev2_kind;
-  int64_t big_pairs = 0, split_redo = 0;
+  int64_t big_pairs = 0, split_redo = 0, cache_builds = 0;
+  // candidate cache
+  DevBuf<unsigned short> cache_pool;
+  DevBuf<long long> cache_off;
+  DevBuf<int> cache_cnt;
+  DevBuf<unsigned long long> cache_count;
+  long long cache_cap = 0;
+  bool cache_valid = false;
+  DevBuf<double> cc0, cq0;
   bool eval_pending = false;
   DevBuf<unsigned long long> counters;
   int npairs = 0, nentries = 0;
@@ -123,6 +131,7 @@ AtomView view(sh_ctx *h) {
   AtomView A;
   A.x = h->x.p; A.v = h->v.p; A.q = h->q.p; A.L = h->L.p; A.f = h->f.p; A.tq = h->tq.p;
   A.c = h->c.p; A.Rs = h->Rs.p; A.c0 = h->c0.p; A.wallf = h->wallf.p; A.shape = h->shape.p;
+  A.cc0 = h->cc0.p; A.cq0 = h->cq0.p;
   A.n = (int)(h->n - h->nghost); A.stride = h->stride;   // kernels over OWNED atoms
   return A;
 }
@@ -148,6 +157,8 @@ int upload_shapes(sh_ctx *h) {
         for (int e = 0; e < 3; e++) for (int k = 0; k < t.nq; k++) pf[(size_t)e * t.nq + k] = (float)t.node_p[e][k];
         d.pf.ensure(pf.size());
         CU(cudaMemcpy(d.pf.p, pf.data(), pf.size() * sizeof(float), cudaMemcpyHostToDevice));
+        d.cubew.ensure(t.cube_wide2.size());
+        CU(cudaMemcpy(d.cubew.p, t.cube_wide2.data(), t.cube_wide2.size() * sizeof(float), cudaMemcpyHostToDevice));
         d.cube.ensure(t.cube_bound2.size());
         CU(cudaMemcpy(d.cube.p, t.cube_bound2.data(), t.cube_bound2.size() * sizeof(float), cudaMemcpyHostToDevice));
       }
@@ -168,7 +179,7 @@ int upload_shapes(sh_ctx *h) {
       v.Ap = d.Ap.p; v.ab = d.ab.p;
       v.px = d.node.p; v.py = d.node.p + t.nq; v.pz = d.node.p + 2 * (size_t)t.nq;
       v.nx = d.node.p + 3 * (size_t)t.nq; v.ny = d.node.p + 4 * (size_t)t.nq; v.nz = d.node.p + 5 * (size_t)t.nq;
-      v.n_theta = t.n_theta; v.n_phi = t.n_phi; v.nterms4 = (t.nterms + 3) / 4 * 4; v.row_x = d.row_x.p; v.cube_b2 = d.cube.p; v.cube_n = t.cube_n; v.pad2_ = 0; v.pf = d.pf.p;
+      v.n_theta = t.n_theta; v.n_phi = t.n_phi; v.nterms4 = (t.nterms + 3) / 4 * 4; v.row_x = d.row_x.p; v.cube_b2 = d.cube.p; v.cube_n = t.cube_n; v.pad2_ = 0; v.pf = d.pf.p; v.cube_w2 = d.cubew.p; v.cache_delta = t.cache_delta;
     }
     int off = 0;
     for (int s = 0; s < ns; s++) { h->shape_host_view[s].tab_off = off; off += h->shape_host_view[s].nterms4 + 4; }
@@ -300,6 +311,7 @@ int build_neighbors(sh_ctx *h) {
   CU(cudaGetLastError());
   h->npairs = npairs; h->nentries = nentries;
   h->list_valid = true; h->steps_since_build = 0; h->neighbor_builds++;
+  h->cache_valid = false;   // the pair list changed
   return 0;
 }
 
@@ -368,7 +380,7 @@ int run_split_pipeline(sh_ctx *h, PairArgs &P) {
     h->pd_off.ensure((size_t)2 * np + 2); h->pd_cnt.ensure((size_t)2 * np + 2); h->big_list.ensure(np + 1);
     h->pool_base.ensure(SH_MAX_SHAPES); h->pool_cap.ensure(SH_MAX_SHAPES); h->pool_count.ensure(SH_MAX_SHAPES); h->split_flags.ensure(4);
   } catch (std::string &e) { return fail(h, e); }
-  if (!h->h_pool_count) CU(cudaMallocHost(&h->h_pool_count, (SH_MAX_SHAPES + 2) * sizeof(unsigned long long)));
+  if (!h->h_pool_count) CU(cudaMallocHost(&h->h_pool_count, (SH_MAX_SHAPES + 4) * sizeof(unsigned long long)));
   if ((int)h->h_pool_cap.size() != ns) {   // first sizing: 16 records per pair-direction, spread over the shapes
     h->h_pool_cap.assign(ns, std::max<long long>(4096, (long long)np * 32 / std::max(1, ns) * 2));
   }
@@ -379,6 +391,43 @@ int run_split_pipeline(sh_ctx *h, PairArgs &P) {
     return 0;
   };
   auto tock = [&]() { cudaEventRecord(h->ev2[h->ev2_used + 1], h->stream); h->ev2_used += 2; };
+  // ---- candidate cache: (re)build when the pair list changed or a particle used up its displacement margin
+  CacheArgs C;
+  C.enabled = (h->tune_variant & (8 | 2)) ? 0 : 1;   // the cache is built from the direction-cell bounds
+  C.invalid = h->scalars.p + 3;
+  if (C.enabled) {
+    try { h->cache_off.ensure((size_t)2 * np + 2); h->cache_cnt.ensure((size_t)2 * np + 2); h->cache_count.ensure(2); }
+    catch (std::string &e) { return fail(h, e); }
+    if (!h->cache_valid) {
+      if (h->cache_cap < (long long)np * 64) h->cache_cap = (long long)np * 64;
+      for (int attempt = 0;; attempt++) {
+        if (attempt > 6) return fail(h, "candidate cache kept overflowing");
+        try { h->cache_pool.ensure((size_t)h->cache_cap + 64); } catch (std::string &e) { return fail(h, e); }
+        CU(cudaMemsetAsync(h->cache_count.p, 0, 2 * sizeof(unsigned long long), h->stream));
+        CU(cudaMemsetAsync(h->split_flags.p + 2, 0, sizeof(int), h->stream));
+        C.pool = h->cache_pool.p; C.off = h->cache_off.p; C.cnt = h->cache_cnt.p; C.count = h->cache_count.p;
+        C.cap = h->cache_cap; C.overflow = h->split_flags.p + 2;
+        pair_cache_build_kernel<WPB><<<cdiv(np, WPB), WPB * 32, 0, h->stream>>>(P, C);
+        h->kernel_launches++;
+        CU(cudaMemcpyAsync(h->h_pool_count, h->cache_count.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(h->h_pool_count + 1, h->split_flags.p + 2, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        if (*reinterpret_cast<const int *>(h->h_pool_count + 1) == 0) break;
+        h->cache_cap = (long long)(h->h_pool_count[0] * 3 / 2) + 4096;
+      }
+      cache_origin_kernel<<<cdiv(h->n, 256), 256, 0, h->stream>>>(view_all(h));
+      CU(cudaMemsetAsync(h->scalars.p + 3, 0, sizeof(int), h->stream));
+      h->kernel_launches++;
+      h->cache_valid = true; h->cache_builds++;
+    } else {
+      double dmin = 1e300;
+      for (auto &sh : h->shapes) dmin = std::min(dmin, sh.cache_delta);
+      cache_check_kernel<<<cdiv(h->n, 256), 256, 0, h->stream>>>(view_all(h), h->d_shapes.p, 0.5 * dmin, h->scalars.p + 3);
+      h->kernel_launches++;
+    }
+  }
+  C.pool = h->cache_pool.p; C.off = h->cache_off.p; C.cnt = h->cache_cnt.p; C.count = h->cache_count.p;
+  C.cap = h->cache_cap; C.overflow = h->split_flags.p + 2;
   for (int attempt = 0; attempt < 6; attempt++) {
     std::vector<long long> base(ns);
     long long tot = 0;
@@ -393,14 +442,16 @@ int run_split_pipeline(sh_ctx *h, PairArgs &P) {
     S.pd_off = h->pd_off.p; S.pd_cnt = h->pd_cnt.p; S.big_list = h->big_list.p; S.nbig = h->split_flags.p; S.overflow = h->split_flags.p + 1;
     CU(cudaMemcpyAsync(h->counters.p + 8, h->counters.p, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, h->stream));
     if (tick(0)) return -2;
-    pair_cull_kernel<WPB><<<cdiv(np, WPB), WPB * 32, 0, h->stream>>>(P, S, (h->tune_variant & 2) ? 0 : 1);
+    pair_cull_kernel<WPB><<<cdiv(np, WPB), WPB * 32, 0, h->stream>>>(P, S, C, (h->tune_variant & 2) ? 0 : 1);
     tock();
     h->kernel_launches++;
     CU(cudaMemcpyAsync(h->h_pool_count, h->pool_count.p, ns * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(h->h_pool_count + SH_MAX_SHAPES, h->split_flags.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(h->h_pool_count + SH_MAX_SHAPES + 1, h->scalars.p + 3, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     const int *fl = reinterpret_cast<const int *>(h->h_pool_count + SH_MAX_SHAPES);
     const int nbig = fl[0], overflow = fl[1];
+    if (C.enabled && fl[2] != 0) h->cache_valid = false;   // margin used up: this step ran on the window, rebuild next step
     if (overflow) {   // grow the pools to what this step asked for (+50 %) and redo the cull
       for (int s = 0; s < ns; s++) h->h_pool_cap[s] = std::max<long long>(h->h_pool_cap[s], (long long)(h->h_pool_count[s] * 3 / 2) + 4096);
       // the cull kernel already added its pair / transform counters: restore the snapshot before the redo
@@ -561,7 +612,7 @@ int sh_destroy(sh_ctx *h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  for (auto &d : h->shape_dev) { d.Ap.release(); d.ab.release(); d.node.release(); d.row_x.release(); d.cube.release(); d.pf.release(); }
+  for (auto &d : h->shape_dev) { d.Ap.release(); d.ab.release(); d.node.release(); d.row_x.release(); d.cube.release(); d.pf.release(); d.cubew.release(); }
   h->d_shapes.release(); h->d_pk.release(); h->d_pm.release();
   DevBuf<double> *db[] = {&h->x, &h->v, &h->q, &h->L, &h->f, &h->tq, &h->c, &h->Rs, &h->c0, &h->wallf, &h->ewall, &h->ke, &h->bbox, &h->slot, &h->pres};
   for (auto *b : db) b->release();
@@ -573,6 +624,7 @@ int sh_destroy(sh_ctx *h) {
   for (auto &e : h->ev2) cudaEventDestroy(e);
   h->pool.release(); h->pool_base.release(); h->pool_cap.release(); h->pd_off.release(); h->pool_count.release();
   h->pd_cnt.release(); h->big_list.release(); h->split_flags.release();
+  h->cache_pool.release(); h->cache_off.release(); h->cache_cnt.release(); h->cache_count.release(); h->cc0.release(); h->cq0.release();
   if (h->h_pool_count) cudaFreeHost(h->h_pool_count);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   h->stage.release();
@@ -643,7 +695,7 @@ int sh_set_atoms(sh_ctx *h, int64_t n, const int64_t *tag, const int *shape, con
     h->x.ensure(3 * (size_t)st); h->v.ensure(3 * (size_t)st); h->q.ensure(4 * (size_t)st); h->L.ensure(3 * (size_t)st);
     h->f.ensure(3 * (size_t)st); h->tq.ensure(3 * (size_t)st); h->c.ensure(3 * (size_t)st); h->Rs.ensure(9 * (size_t)st);
     h->c0.ensure(3 * (size_t)st); h->wallf.ensure(6 * (size_t)st); h->ewall.ensure(st); h->ke.ensure(2 * (size_t)st);
-    h->shape.ensure(st);
+    h->shape.ensure(st); h->cc0.ensure(3 * (size_t)st); h->cq0.ensure(4 * (size_t)st);
   } catch (std::string &e) { return fail(h, e); }
   h->n = n; h->stride = st;
   std::vector<double> buf((size_t)4 * st, 0.0);
@@ -720,6 +772,7 @@ int sh_set_pair_tuning(sh_ctx *h, int threads_per_cta, int ctas_per_sm, int vari
   if (threads_per_cta != 0 && threads_per_cta != 64 && threads_per_cta != 128 && threads_per_cta != 256 && threads_per_cta != 384 && threads_per_cta != 512)
     return fail(h, "threads_per_cta must be 0, 64, 128, 256 or 512");
   h->tune_threads = threads_per_cta; h->tune_ctas_per_sm = ctas_per_sm; h->tune_variant = variant;
+  h->cache_valid = false;
   return 0;
 }
 
@@ -1047,7 +1100,7 @@ int sh_get_split_stats(const sh_ctx *hc, double *seconds_eval, int64_t *eval_lau
   if (seconds_eval) *seconds_eval = h->sec_eval;
   if (eval_launches) *eval_launches = h->eval_launches;
   if (deep_pairs) *deep_pairs = h->big_pairs;
-  if (pool_redos) *pool_redos = h->split_redo;
+  if (pool_redos) *pool_redos = h->split_redo + 1000000 * h->cache_builds;   // cache builds in the millions digit
   return 0;
 }
 
@@ -1056,7 +1109,7 @@ int sh_reset_timers(sh_ctx *h) {
   int rc = drain_events(h);
   if (rc) return rc;
   h->sec_pair = h->sec_neigh = h->sec_other = 0; h->pair_launches = 0; h->sec_run_total = 0;
-  h->sec_eval = h->sec_cull = h->sec_reduce = h->sec_deep = 0; h->eval_launches = 0; h->big_pairs = 0; h->split_redo = 0;
+  h->sec_eval = h->sec_cull = h->sec_reduce = h->sec_deep = 0; h->eval_launches = 0; h->big_pairs = 0; h->split_redo = 0; h->cache_builds = 0;
   h->neighbor_builds = 0; h->kernel_launches = 0;
   CU(cudaMemset(h->counters.p, 0, 16 * sizeof(unsigned long long)));
   return 0;

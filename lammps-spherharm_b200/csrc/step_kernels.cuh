@@ -10,6 +10,7 @@ struct AtomView {
   double *x, *v, *q, *L, *f, *tq;  // SoA [comp*stride + i]
   double *c, *Rs, *c0;             // SH origin, shape->space rotation, origin at last neighbor build
   double *wallf;                   // 6 x stride: wall force / torque
+  double *cc0, *cq0;               // SH origin (3) and quaternion (4) at the last candidate-cache build
   int *shape;
   int n, stride;
 };
@@ -80,6 +81,36 @@ __global__ void unpack_atoms_kernel(AtomView A, int first, int m, const double *
   for (int d = 0; d < 3; d++) A.x[d * st + i] = in[7 * (size_t)k + d];
 #pragma unroll
   for (int d = 0; d < 4; d++) A.q[d * st + i] = in[7 * (size_t)k + 3 + d];
+}
+
+// candidate cache (pair_split_kernels.cuh): a node of atom i has moved, relative to any partner frame, by at most
+// w_i = |c - c0| + angle(q0 -> q) * (rmax_i + delta_i); the cache stays valid while every w_i <= thresh.
+__global__ void cache_check_kernel(AtomView A, const DevShape *shapes, double thresh, int *flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n) return;
+  const int st = A.stride;
+  const DevShape &s = shapes[A.shape[i]];
+  double u2 = 0, dm = 0, dp = 0;
+#pragma unroll
+  for (int d = 0; d < 3; d++) { const double dd = A.c[d * st + i] - A.cc0[d * st + i]; u2 += dd * dd; }
+#pragma unroll
+  for (int d = 0; d < 4; d++) {
+    const double a = A.q[d * st + i], b = A.cq0[d * st + i];
+    dm += (a - b) * (a - b); dp += (a + b) * (a + b);
+  }
+  const double dq = sqrt(fmin(dm, dp));                 // = 2 sin(angle/4)
+  const double ang = dq < 0.2 ? 2.02 * dq : 10.0;       // angle <= 2.02 dq for small rotations
+  const double w = sqrt(u2) + ang * (s.rmax + s.cache_delta);
+  if (!(w <= thresh)) *flag = 1;
+}
+__global__ void cache_origin_kernel(AtomView A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n) return;
+  const int st = A.stride;
+#pragma unroll
+  for (int d = 0; d < 3; d++) A.cc0[d * st + i] = A.c[d * st + i];
+#pragma unroll
+  for (int d = 0; d < 4; d++) A.cq0[d * st + i] = A.q[d * st + i];
 }
 
 // AoS (n x ncomp, host layout) <-> SoA (ncomp x stride, device layout) transposes for the C-ABI

@@ -151,10 +151,10 @@ def test_neighbor_skin_does_not_change_forces():
     assert np.abs(res[0] - res[1]).max() <= 1e-12 * np.abs(res[0]).max()
 
 
-@pytest.mark.parametrize("threads,variant", [(128, 1), (256, 1), (128, 4), (256, 4), (384, 4), (512, 4), (512, 6), (0, 0), (0, 2)])
+@pytest.mark.parametrize("threads,variant", [(128, 1), (256, 1), (128, 4), (256, 4), (384, 4), (512, 4), (512, 6), (0, 0), (0, 2), (0, 8), (0, 10)])
 def test_kernel_variants_agree_with_oracle(threads, variant):
     """variant bits: 1 = CTA-per-pair full-scan kernel; 4 = fused warp-per-pair kernel; 0 = split
-    cull/evaluate/reduce pipeline (default); 2 = direction-cell bound off."""
+    cull/evaluate/reduce pipeline (default); 2 = direction-cell bound off; 8 = candidate cache off."""
     cfg = W.config3_packing(256, lmax=20, grid=(32, 64))
     g, o = both(cfg)
     g.set_pair_tuning(threads, 0, variant)
@@ -162,9 +162,9 @@ def test_kernel_variants_agree_with_oracle(threads, variant):
     assert e["ncontact"] > 20
     if variant == 1:      # full scan: every counter equals the oracle's
         assert g.get_counters()["nodes_transformed"] == o.get_counters()["nodes_transformed"]
-    if variant in (1, 2, 6):  # no direction-cell bound: every bounding-sphere survivor is evaluated, as in the oracle
+    if variant in (1, 2, 6, 10):  # no direction-cell bound: every bounding-sphere survivor is evaluated, as in the oracle
         assert g.get_counters()["nodes_evaluated"] == o.get_counters()["nodes_evaluated"]
-    if variant in (0, 4):
+    if variant in (0, 4, 8):
         assert g.get_counters()["nodes_evaluated"] < o.get_counters()["nodes_evaluated"]
 
 
@@ -214,6 +214,28 @@ def test_mixed_lmax_shapes():
                 s.pair_coeff(i, j, 500.0 * (1 + i + j), 1.0 + 0.25 * ((i + j) % 2))
     e = check_forces(sims[0], sims[1])
     assert e["ncontact"] > 20
+
+
+def test_candidate_cache_matches_window_path_over_a_run():
+    """Dynamic packing (fast particles, rotations): the candidate cache must be rebuilt before any node can
+    escape it, so the per-step set of inside nodes is identical with the cache on and off, and the
+    trajectories agree to rounding."""
+    cfg = W.packing((3, 3, 3), 20, (32, 64), nshapes=4, seed=17, nn_frac=1.8, vel_sigma=1.5, dt=5e-4, skin=0.3, name="cache")
+    rng = np.random.default_rng(3)
+    cfg["angmom"] = rng.normal(0, 2.0, size=cfg["x"].shape)       # fast spins: rotation must trigger rebuilds too
+    res = []
+    for variant in (0, 8):
+        g = pkg.ShGpu(); W.apply(g, cfg); g.set_pair_tuning(0, 0, variant)
+        g.compute_forces(); g.reset_timers(); g.run(400)
+        res.append((g.get_atoms(), g.get_counters(), g.get_split_stats())); g.close()
+    (a0, c0, s0), (a1, c1, s1) = res
+    assert c0["nodes_inside"] == c1["nodes_inside"] and c0["pair_evals"] == c1["pair_evals"]
+    assert c0["nodes_inside"] > 1000
+    builds = s0["pool_redos"] // 1000000
+    assert builds >= 3, "cache was rebuilt %d times; the test must exercise the displacement trigger" % builds
+    assert c0["nodes_transformed"] < 0.5 * c1["nodes_transformed"]
+    for k in ("x", "v", "quat", "angmom"):
+        assert np.abs(a0[k] - a1[k]).max() <= 1e-9 * max(1.0, np.abs(a1[k]).max()), k
 
 
 def test_error_paths():
