@@ -20,7 +20,7 @@
 
 namespace shgpu {
 
-#define SPLIT_CAP 64
+#define SPLIT_CAP 88
 
 struct __align__(16) SurvRec {
   double s0, s1, s2;
@@ -236,13 +236,13 @@ __global__ void __launch_bounds__(WPB * 32, 4) pair_cache_build_kernel(PairArgs 
 // ---- A: cull.  Per (pair, direction): candidates (from the cache, else from the window + FP32 pre-cull) ->
 // exact FP64 stage on full warps -> survivor records -> one contiguous run in the target shape's pool.
 template <int WPB>
-__global__ void __launch_bounds__(WPB * 32, 3) pair_cull_kernel(PairArgs A, SplitArgs S, CacheArgs C, int use_bounds) {
+__global__ void __launch_bounds__(WPB * 32, 4) pair_cull_kernel(PairArgs A, SplitArgs S, CacheArgs C, int use_bounds) {
   __shared__ __align__(16) SurvRec s_rec[WPB][2][SPLIT_CAP];
   __shared__ double s_pose[WPB][16];
   __shared__ unsigned short s_cand[WPB][64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int p = blockIdx.x * WPB + warp;
-  if (p >= A.npairs) return;
+  if (p < A.npairs) {
   const int st = A.stride;
   const int i = A.pair_i[p], j = A.pair_j[p];
   double d[3];
@@ -383,8 +383,8 @@ __global__ void __launch_bounds__(WPB * 32, 3) pair_cull_kernel(PairArgs A, Spli
       S.pd_cnt[2 * p] = -1; S.pd_cnt[2 * p + 1] = -1;
       S.big_list[atomicAdd(S.nbig, 1)] = p;
     }
-    return;   // counters of a deep pair are accumulated by the fused kernel that re-does it
-  }
+    // counters of a deep pair are accumulated by the fused kernel that re-does it
+  } else {
 #pragma unroll
   for (int dir = 0; dir < 2; dir++) {
     const int sb_id = dir ? shp_i : shp_j;
@@ -398,11 +398,13 @@ __global__ void __launch_bounds__(WPB * 32, 3) pair_cull_kernel(PairArgs A, Spli
     } else if (lane == 0) *S.overflow = 1;
     if (lane == 0) { S.pd_off[2 * p + dir] = base; S.pd_cnt[2 * p + dir] = fits ? cnt[dir] : 0; }
   }
-  if (lane == 0) {
+  if (lane == 0) {   // no block barrier here: warps must retire independently (pairs differ a lot in length)
     atomicAdd(&A.counters[0], 1ull);
     atomicAdd(&A.counters[1], n_trans);
     if (j >= A.nlocal) atomicAdd(&A.counters[4], 1ull);
   }
+  }  // !big
+  }  // p < npairs
 }
 
 // ---- B: evaluate pooled records.  blockIdx -> (shape, first record) through blk_start (prefix of CTA counts)
@@ -424,9 +426,12 @@ __global__ void __launch_bounds__(WPB * 32) pair_eval_kernel(const DevShape *sha
   for (int t = threadIdx.x; t < sh.nterms4 + 4; t += WPB * 32) { s_ab[t] = sh.ab[t]; s_Ap[t] = sh.Ap[t]; }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ unsigned long long s_nev;
+  if (threadIdx.x == 0) s_nev = 0;
+  __syncthreads();
   const long long n = P.count[s];
   const long long r0 = ((long long)(blockIdx.x - P.blk_start[s]) * WPB + warp) * 64;
-  if (r0 >= n) return;
+  if (r0 < n) {
   SurvRec *rec = S.pool + S.pool_base[s];
   const long long ia = r0 + lane, ib = r0 + 32 + lane;
   const bool va = ia < n, vb = ib < n;
@@ -450,7 +455,10 @@ __global__ void __launch_bounds__(WPB * 32) pair_eval_kernel(const DevShape *sha
     if (ra.flag != 2) { rec[ia].flag = rho < r ? 1 : 0; nev++; }
   }
   nev = __reduce_add_sync(0xffffffffu, nev);   // records preset by A (flag 2) are not "evaluated"
-  if (lane == 0 && nev) { atomicAdd(&counters[2], (unsigned long long)nev); atomicAdd(&counters[5], (unsigned long long)nev); }
+  if (lane == 0 && nev) atomicAdd(&s_nev, (unsigned long long)nev);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_nev) { atomicAdd(&counters[2], s_nev); atomicAdd(&counters[5], s_nev); }
 }
 
 // ---- C: per-pair reduction + contact law.  One THREAD per pair: the two record runs are
