@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(WPB * 32, 4) pair_cache_build_kernel(PairArgs 
 // ---- A: cull.  Per (pair, direction): candidates (from the cache, else from the window + FP32 pre-cull) ->
 // exact FP64 stage on full warps -> survivor records -> one contiguous run in the target shape's pool.
 template <int WPB>
-__global__ void __launch_bounds__(WPB * 32, 4) pair_cull_kernel(PairArgs A, SplitArgs S, CacheArgs C, int use_bounds) {
+__global__ void __launch_bounds__(WPB * 32, 32 / WPB) pair_cull_kernel(PairArgs A, SplitArgs S, CacheArgs C, int use_bounds) {
   __shared__ __align__(16) SurvRec s_rec[WPB][2][SPLIT_CAP];
   __shared__ double s_pose[WPB][16];
   __shared__ unsigned short s_cand[WPB][64];

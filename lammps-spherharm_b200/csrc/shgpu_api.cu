@@ -442,7 +442,7 @@ int run_split_pipeline(sh_ctx *h, PairArgs &P) {
     S.pd_off = h->pd_off.p; S.pd_cnt = h->pd_cnt.p; S.big_list = h->big_list.p; S.nbig = h->split_flags.p; S.overflow = h->split_flags.p + 1;
     CU(cudaMemcpyAsync(h->counters.p + 8, h->counters.p, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, h->stream));
     if (tick(0)) return -2;
-    pair_cull_kernel<WPB><<<cdiv(np, WPB), WPB * 32, 0, h->stream>>>(P, S, C, (h->tune_variant & 2) ? 0 : 1);
+    pair_cull_kernel<1><<<np, 32, 0, h->stream>>>(P, S, C, (h->tune_variant & 2) ? 0 : 1);   // small CTAs: pairs differ in length
     tock();
     h->kernel_launches++;
     CU(cudaMemcpyAsync(h->h_pool_count, h->pool_count.p, ns * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
