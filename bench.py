@@ -220,9 +220,9 @@ def run_graft(args):
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
-    barrier()
     if rank == 0:
-        sampler.start()
+        sampler.start()     # before the barrier: its start-up delay must not sit inside any rank's timed region
+    barrier()
     t0 = time.perf_counter()
     nreb = 0
     if dd is not None:
