@@ -197,7 +197,7 @@ def run_graft(args):
     dd = None
     sim = pkg.ShGpu(device=local)
     if use_dist:
-        cfg = make_workload(args, pkg, args.particles * world)
+        cfg = make_workload(args, pkg, args.particles if args.strong else args.particles * world)
         D = pkg.load_decomp()
         dd = D.DomainDecomposition(sim, cfg, comm_device="cuda")
         n = dd.nlocal
@@ -311,7 +311,7 @@ def run_graft(args):
         cpu = cpu_baseline_run(args, pkg, budget_s=args.cpu_budget, steps=1, warmup=0) if (world == 1 and not args.no_cpu) else None
         line = {"metric": METRIC, "value": pairs_total / dev_s_max, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * dev_s_max / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": dict(workload_config(args, n_global), parallelism=("single GPU" if world == 1 else
                                "spatial decomposition %s bricks, NCCL all_to_all ghost exchange every step, %d rebuilds"
                                % ("x".join(str(v) for v in dd.pgrid), nreb))),
@@ -345,6 +345,7 @@ def main():
     ap.add_argument("--lmax", type=int, default=30)
     ap.add_argument("--ntheta", type=int, default=48)
     ap.add_argument("--nphi", type=int, default=96)
+    ap.add_argument("--strong", action="store_true", help="N>1: keep the TOTAL particle count at --particles (strong scaling)")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
