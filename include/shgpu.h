@@ -115,7 +115,9 @@ int sh_get_split_stats(const sh_ctx *h, double *seconds_eval, int64_t *eval_laun
 /* device time of sh_run (events on the library's stream bracketing all steps of the call) -------- */
 int sh_get_run_time(const sh_ctx *h, double *seconds_last_run, double *seconds_total);
 
-/* tuning knobs of the pair kernel (block size, CTAs per SM); 0 = default ---------------------- */
+/* tuning knobs of the pair phase; 0 = default.  variant bits: 1 CTA-per-pair full-scan kernel, 2 direction-cell
+ * bound off, 4 fused warp-per-pair kernel, 8 candidate cache off, 16 force the split pipeline (systems with fewer
+ * than 16384 pairs default to the fused kernel) -------------------------------------------------- */
 int sh_set_pair_tuning(sh_ctx *h, int threads_per_cta, int ctas_per_sm, int variant);
 
 /* FP64 FMA-pipe peak microbenchmark (K0): returns measured DFMA flop/s of the device ----------- */

@@ -525,7 +525,9 @@ int compute_forces_device(sh_ctx *h) {
       if (nt == 256) rc = launch_pair<256>(h, P, h->tune_ctas_per_sm, pair_smem_bytes(maxT, maxq, 8));
       else if (nt == 64) rc = launch_pair<64>(h, P, h->tune_ctas_per_sm, pair_smem_bytes(maxT, maxq, 2));
       else rc = launch_pair<128>(h, P, h->tune_ctas_per_sm, pair_smem_bytes(maxT, maxq, 4));
-    } else if (h->tune_variant & 4) {    // fused warp-per-pair kernel
+    } else if ((h->tune_variant & 4) || (!(h->tune_variant & 16) && h->npairs < 16384)) {
+      // fused warp-per-pair kernel: explicit (bit 4), or small systems where the split pipeline's extra
+      // launches and its host sync cost more than they save (bit 16 forces the split pipeline)
       rc = launch_fused(h, P);
     } else {                             // split pipeline (default): cull / evaluate / reduce
       rc = run_split_pipeline(h, P);

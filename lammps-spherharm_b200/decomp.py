@@ -161,18 +161,28 @@ class DomainDecomposition:
         send_rows = [[] for _ in range(self.world)]
         send_idx = [[] for _ in range(self.world)]
         send_shift = [[] for _ in range(self.world)]
+        # only atoms in the shell within rc of a decomposed face can be ghosts of anybody
+        near_hi = [x[:, d] >= self.myhi[d] - self.rc if self.pgrid[d] > 1 else None for d in range(3)]
+        near_lo = [x[:, d] < self.mylo[d] + self.rc if self.pgrid[d] > 1 else None for d in range(3)]
+        shell_mask = np.zeros(nloc, dtype=bool)
+        for d in range(3):
+            if self.pgrid[d] > 1:
+                shell_mask |= near_hi[d] | near_lo[d]
+        shell = np.nonzero(shell_mask)[0]
+        sh_hi = [near_hi[d][shell] if near_hi[d] is not None else None for d in range(3)]
+        sh_lo = [near_lo[d][shell] if near_lo[d] is not None else None for d in range(3)]
         for o in OFFSETS:
             nb = self._neighbor(o)
             if nb is None:
                 continue
             dest, shift = nb
-            m = np.ones(nloc, dtype=bool)
+            m = np.ones(len(shell), dtype=bool)
             for d in range(3):
                 if o[d] == 1:
-                    m &= x[:, d] >= self.myhi[d] - self.rc
+                    m &= sh_hi[d]
                 elif o[d] == -1:
-                    m &= x[:, d] < self.mylo[d] + self.rc
-            idx = np.nonzero(m)[0]
+                    m &= sh_lo[d]
+            idx = shell[m]
             if len(idx) == 0:
                 continue
             send_idx[dest].append(idx)

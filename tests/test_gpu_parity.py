@@ -151,10 +151,11 @@ def test_neighbor_skin_does_not_change_forces():
     assert np.abs(res[0] - res[1]).max() <= 1e-12 * np.abs(res[0]).max()
 
 
-@pytest.mark.parametrize("threads,variant", [(128, 1), (256, 1), (128, 4), (256, 4), (384, 4), (512, 4), (512, 6), (0, 0), (0, 2), (0, 8), (0, 10)])
+@pytest.mark.parametrize("threads,variant", [(128, 1), (256, 1), (128, 4), (256, 4), (384, 4), (512, 4), (512, 6), (0, 0), (0, 16), (0, 18), (0, 24), (0, 26)])
 def test_kernel_variants_agree_with_oracle(threads, variant):
     """variant bits: 1 = CTA-per-pair full-scan kernel; 4 = fused warp-per-pair kernel; 0 = split
-    cull/evaluate/reduce pipeline (default); 2 = direction-cell bound off; 8 = candidate cache off."""
+    cull/evaluate/reduce pipeline (default); 2 = direction-cell bound off; 8 = candidate cache off;
+    16 = force the split pipeline (small systems default to the fused kernel)."""
     cfg = W.config3_packing(256, lmax=20, grid=(32, 64))
     g, o = both(cfg)
     g.set_pair_tuning(threads, 0, variant)
@@ -162,9 +163,9 @@ def test_kernel_variants_agree_with_oracle(threads, variant):
     assert e["ncontact"] > 20
     if variant == 1:      # full scan: every counter equals the oracle's
         assert g.get_counters()["nodes_transformed"] == o.get_counters()["nodes_transformed"]
-    if variant in (1, 2, 6, 10):  # no direction-cell bound: every bounding-sphere survivor is evaluated, as in the oracle
+    if variant in (1, 2, 6, 18, 26):  # no direction-cell bound: every bounding-sphere survivor is evaluated, as in the oracle
         assert g.get_counters()["nodes_evaluated"] == o.get_counters()["nodes_evaluated"]
-    if variant in (0, 4, 8):
+    if variant in (0, 4, 16, 24):
         assert g.get_counters()["nodes_evaluated"] < o.get_counters()["nodes_evaluated"]
 
 
@@ -224,7 +225,7 @@ def test_candidate_cache_matches_window_path_over_a_run():
     rng = np.random.default_rng(3)
     cfg["angmom"] = rng.normal(0, 2.0, size=cfg["x"].shape)       # fast spins: rotation must trigger rebuilds too
     res = []
-    for variant in (0, 8):
+    for variant in (16, 24):
         g = pkg.ShGpu(); W.apply(g, cfg); g.set_pair_tuning(0, 0, variant)
         g.compute_forces(); g.reset_timers(); g.run(400)
         res.append((g.get_atoms(), g.get_counters(), g.get_split_stats())); g.close()
