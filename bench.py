@@ -32,6 +32,7 @@ sys.path.insert(0, ROOT)
 
 import shpkg  # noqa: E402
 
+EVAL_DRAM_BYTES_PER_RECORD = 36.6   # measured, see the roofline.traffic note below
 METRIC = "contact_pair_evals_per_s"
 UNIT = "pair-evals/s"
 
@@ -292,7 +293,12 @@ def run_graft(args):
         achieved = ev_flops / ev_s / 1e12
         kshare = {k: v / max(pair_s, 1e-12) for k, v in st_t.items()}
         roofline = {"bound": "fp64", "kernel": "pair_eval_kernel", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": achieved / peak_tf, "traffic": None,
+                    "frac": achieved / peak_tf,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of pair_eval_kernel from one ncu --set full capture
+                    # (profiles/r01_eval_kernel_ncu_summary.txt) expressed per record and scaled to this run's records
+                    # per launch; algorithmic bytes are 33 per record (32 B record in, 1 B flag out)
+                    "traffic": EVAL_DRAM_BYTES_PER_RECORD * float(ev_nodes) / max(1, tim["pair_launches"]),
+                    "traffic_source": "ncu capture r01, %.1f B/record" % EVAL_DRAM_BYTES_PER_RECORD,
                     "eval_kernel_avg_launch_ms": 1e3 * ev_s / max(1, tim["pair_launches"]),
                     "eval_kernel_flops_per_launch": ev_flops / max(1, tim["pair_launches"]),
                     "pair_phase": {"achieved_tflops": phase_achieved, "frac": phase_achieved / peak_tf,

@@ -104,14 +104,14 @@ int sh_get_timers(const sh_ctx *h, double *seconds_pair, int64_t *pair_launches,
                   double *seconds_neigh, double *seconds_other);
 int sh_reset_timers(sh_ctx *h);
 /* split pair pipeline: device time of the SH-evaluation kernel, its launches, pairs routed to the fused
- * deep-contact kernel, survivor-pool regrowths */
+ * deep-contact kernel, survivor-pool regrowths, candidate-cache builds */
 /* raw device counters: 0 pairs, 1 nodes transformed, 2 evaluated, 3 inside, 4 pairs with a ghost, 5 evaluated by
  * pair_eval_kernel (the rest of [2] comes from the fused deep-contact kernel) */
 int sh_get_counter_raw(const sh_ctx *h, int index, int64_t *value);
 int sh_get_split_times(const sh_ctx *h, double *seconds_cull, double *seconds_eval, double *seconds_reduce,
                        double *seconds_deep);
 int sh_get_split_stats(const sh_ctx *h, double *seconds_eval, int64_t *eval_launches, int64_t *deep_pairs,
-                       int64_t *pool_redos);
+                       int64_t *pool_redos, int64_t *cache_builds);
 /* device time of sh_run (events on the library's stream bracketing all steps of the call) -------- */
 int sh_get_run_time(const sh_ctx *h, double *seconds_last_run, double *seconds_total);
 

@@ -251,9 +251,10 @@ class ShGpu:
         return dict(zip(("cull", "eval", "reduce", "deep"), (t.value for t in v)))
 
     def get_split_stats(self):
-        a, b, c, d = C.c_double(), C.c_int64(), C.c_int64(), C.c_int64()
-        self._ck(self.L.sh_get_split_stats(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
-        return dict(seconds_eval=a.value, eval_launches=b.value, deep_pairs=c.value, pool_redos=d.value)
+        a, b, c, d, e = C.c_double(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        self._ck(self.L.sh_get_split_stats(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(e)))
+        return dict(seconds_eval=a.value, eval_launches=b.value, deep_pairs=c.value, pool_redos=d.value,
+                    cache_builds=e.value)
 
     def reset_timers(self):
         self._ck(self.L.sh_reset_timers(self.h))

@@ -30,6 +30,7 @@ struct __align__(16) SurvRec {
 
 struct SplitArgs {
   SurvRec *pool;                  // all shapes' pools in one buffer
+  unsigned char *pool_flag;       // inside flag per record (own array: a flag store must not dirty the 32 B record)
   const long long *pool_base;     // [nshape] first record of the shape's pool
   const long long *pool_cap;      // [nshape]
   unsigned long long *pool_count; // [nshape] records appended this step (may exceed cap -> host grows and reruns)
@@ -394,7 +395,10 @@ __global__ void __launch_bounds__(WPB * 32, 32 / WPB) pair_cull_kernel(PairArgs 
     const bool fits = off + cnt[dir] <= S.pool_cap[sb_id];
     const long long base = S.pool_base[sb_id] + off;
     if (fits) {
-      for (int r = lane; r < cnt[dir]; r += 32) S.pool[base + r] = s_rec[warp][dir][r];
+      for (int r = lane; r < cnt[dir]; r += 32) {
+        S.pool[base + r] = s_rec[warp][dir][r];
+        S.pool_flag[base + r] = (unsigned char)s_rec[warp][dir][r].flag;
+      }
     } else if (lane == 0) *S.overflow = 1;
     if (lane == 0) { S.pd_off[2 * p + dir] = base; S.pd_cnt[2 * p + dir] = fits ? cnt[dir] : 0; }
   }
@@ -433,6 +437,7 @@ __global__ void __launch_bounds__(WPB * 32) pair_eval_kernel(const DevShape *sha
   const long long r0 = ((long long)(blockIdx.x - P.blk_start[s]) * WPB + warp) * 64;
   if (r0 < n) {
   SurvRec *rec = S.pool + S.pool_base[s];
+  unsigned char *flg = S.pool_flag + S.pool_base[s];
   const long long ia = r0 + lane, ib = r0 + 32 + lane;
   const bool va = ia < n, vb = ib < n;
   const int L = sh.lmax;
@@ -445,14 +450,14 @@ __global__ void __launch_bounds__(WPB * 32) pair_eval_kernel(const DevShape *sha
     const double rhoB2 = fma(sB[2], sB[2], fma(sB[1], sB[1], sB[0] * sB[0]));
     double rhoA, rhoB, rA, rB;
     sh_radius_folded_x2(L, s_Ap, s_ab, sA, rhoA2, sB, rhoB2, rhoA, rhoB, rA, rB);
-    if (va && ra.flag != 2) { rec[ia].flag = rhoA < rA ? 1 : 0; nev++; }
-    if (vb && rb.flag != 2) { rec[ib].flag = rhoB < rB ? 1 : 0; nev++; }
+    if (va && ra.flag != 2) { flg[ia] = rhoA < rA ? 1 : 0; nev++; }
+    if (vb && rb.flag != 2) { flg[ib] = rhoB < rB ? 1 : 0; nev++; }
   } else if (va) {
     const SurvRec ra = rec[ia];
     const double rho2 = fma(ra.s2, ra.s2, fma(ra.s1, ra.s1, ra.s0 * ra.s0));
     double rho;
     const double r = sh_radius_folded(L, s_Ap, s_ab, ra.s0, ra.s1, ra.s2, rho2, rho);
-    if (ra.flag != 2) { rec[ia].flag = rho < r ? 1 : 0; nev++; }
+    if (ra.flag != 2) { flg[ia] = rho < r ? 1 : 0; nev++; }
   }
   nev = __reduce_add_sync(0xffffffffu, nev);   // records preset by A (flag 2) are not "evaluated"
   if (lane == 0 && nev) atomicAdd(&s_nev, (unsigned long long)nev);
@@ -505,9 +510,8 @@ __global__ void __launch_bounds__(128, 6) pair_reduce_kernel(PairArgs A, SplitAr
       const double *__restrict__ nodes = sa.px;
       const int nq = sa.nq;
       for (int r = 0; r < cnt; r++) {
-        const int2 kf = *reinterpret_cast<const int2 *>(&S.pool[off + r].k);
-        if (kf.y) {
-          const int k = kf.x;
+        if (S.pool_flag[off + r]) {
+          const int k = S.pool[off + r].k;
           const double p0 = nodes[k], p1 = nodes[nq + k], p2 = nodes[2 * nq + k];
           const double n0 = nodes[3 * nq + k], n1 = nodes[4 * nq + k], n2 = nodes[5 * nq + k];
           const double dp0 = p0 - x0[0], dp1 = p1 - x0[1], dp2 = p2 - x0[2];

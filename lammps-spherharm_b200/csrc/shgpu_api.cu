@@ -81,6 +81,7 @@ struct sh_ctx {
   DevBuf<double> bbox, slot, pres, stage;
   // split pair pipeline (pair_split_kernels.cuh)
   DevBuf<SurvRec> pool;
+  DevBuf<unsigned char> pool_flag;
   DevBuf<long long> pool_base, pool_cap, pd_off;
   DevBuf<unsigned long long> pool_count;
   DevBuf<int> pd_cnt, big_list, split_flags;   // split_flags: [0]=nbig [1]=overflow
@@ -432,13 +433,13 @@ int run_split_pipeline(sh_ctx *h, PairArgs &P) {
     std::vector<long long> base(ns);
     long long tot = 0;
     for (int s = 0; s < ns; s++) { base[s] = tot; tot += h->h_pool_cap[s]; }
-    try { h->pool.ensure((size_t)tot + 64); } catch (std::string &e) { return fail(h, e); }
+    try { h->pool.ensure((size_t)tot + 64); h->pool_flag.ensure((size_t)tot + 64); } catch (std::string &e) { return fail(h, e); }
     CU(cudaMemcpyAsync(h->pool_base.p, base.data(), ns * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->pool_cap.p, h->h_pool_cap.data(), ns * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemsetAsync(h->pool_count.p, 0, SH_MAX_SHAPES * sizeof(unsigned long long), h->stream));
     CU(cudaMemsetAsync(h->split_flags.p, 0, 4 * sizeof(int), h->stream));
     SplitArgs S;
-    S.pool = h->pool.p; S.pool_base = h->pool_base.p; S.pool_cap = h->pool_cap.p; S.pool_count = h->pool_count.p;
+    S.pool = h->pool.p; S.pool_flag = h->pool_flag.p; S.pool_base = h->pool_base.p; S.pool_cap = h->pool_cap.p; S.pool_count = h->pool_count.p;
     S.pd_off = h->pd_off.p; S.pd_cnt = h->pd_cnt.p; S.big_list = h->big_list.p; S.nbig = h->split_flags.p; S.overflow = h->split_flags.p + 1;
     CU(cudaMemcpyAsync(h->counters.p + 8, h->counters.p, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, h->stream));
     if (tick(0)) return -2;
@@ -624,7 +625,7 @@ int sh_destroy(sh_ctx *h) {
   h->counters.release();
   for (auto &e : h->ev) cudaEventDestroy(e);
   for (auto &e : h->ev2) cudaEventDestroy(e);
-  h->pool.release(); h->pool_base.release(); h->pool_cap.release(); h->pd_off.release(); h->pool_count.release();
+  h->pool.release(); h->pool_flag.release(); h->pool_base.release(); h->pool_cap.release(); h->pd_off.release(); h->pool_count.release();
   h->pd_cnt.release(); h->big_list.release(); h->split_flags.release();
   h->cache_pool.release(); h->cache_off.release(); h->cache_cnt.release(); h->cache_count.release(); h->cc0.release(); h->cq0.release();
   if (h->h_pool_count) cudaFreeHost(h->h_pool_count);
@@ -1094,7 +1095,8 @@ int sh_get_split_times(const sh_ctx *hc, double *seconds_cull, double *seconds_e
   return 0;
 }
 
-int sh_get_split_stats(const sh_ctx *hc, double *seconds_eval, int64_t *eval_launches, int64_t *deep_pairs, int64_t *pool_redos) {
+int sh_get_split_stats(const sh_ctx *hc, double *seconds_eval, int64_t *eval_launches, int64_t *deep_pairs, int64_t *pool_redos,
+                       int64_t *cache_builds) {
   sh_ctx *h = const_cast<sh_ctx *>(hc);
   CU(cudaSetDevice(h->device));
   int rc = drain_events(h);
@@ -1102,7 +1104,8 @@ int sh_get_split_stats(const sh_ctx *hc, double *seconds_eval, int64_t *eval_lau
   if (seconds_eval) *seconds_eval = h->sec_eval;
   if (eval_launches) *eval_launches = h->eval_launches;
   if (deep_pairs) *deep_pairs = h->big_pairs;
-  if (pool_redos) *pool_redos = h->split_redo + 1000000 * h->cache_builds;   // cache builds in the millions digit
+  if (pool_redos) *pool_redos = h->split_redo;
+  if (cache_builds) *cache_builds = h->cache_builds;
   return 0;
 }
 

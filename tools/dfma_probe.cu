@@ -11,6 +11,54 @@
 
 using namespace shgpu;
 
+// (kept here only: measured slower than the plain nested loop)
+// Software-pipelined form of sh_radius_folded for tables padded to a multiple of 4 records plus 4
+// (zero records): the coefficient records of the NEXT four terms are fetched while the current
+// four are consumed, so the shared-memory latency is off the dependent chain.  Every term runs the
+// same body; a block (fixed m) starts from the state q1 = 0, q2 = -1, C = S = 0, which makes the
+// generic body reproduce the special first two terms exactly:
+//   l = m   : tx = 0*x,  q = fma(tx, 0, 1) = 1,        C = fma(a, 1, 0) = a
+//   l = m+1 : q = fma(Ap*x, 1, -0) = Ap*x (the rounded product), as in sh_radius_folded.
+// Bit-identical to sh_radius_folded (and to the oracle) up to the sign of a zero accumulator.
+__device__ __forceinline__ double sh_radius_folded_pipe(int L, int nterms4, const double *__restrict__ Ap,
+                                                        const double2 *__restrict__ ab, double s0, double s1,
+                                                        double s2, double rho2, double &rho_out) {
+  const double rho = sqrt(rho2);
+  const double inv = 1.0 / rho;
+  const double x = s2 * inv, zx = s0 * inv, zy = s1 * inv;
+  double u = 1.0, v = 0.0, r = 0.0, C = 0.0, S = 0.0, q1 = 0.0, q2 = -1.0;
+  int m = 0, bend = L;
+  double nA0 = Ap[0], nA1 = Ap[1], nA2 = Ap[2], nA3 = Ap[3];
+  double2 nC0 = ab[0], nC1 = ab[1], nC2 = ab[2], nC3 = ab[3];
+#pragma unroll 1
+  for (int idx = 0; idx < nterms4; idx += 4) {
+    const double cA0 = nA0, cA1 = nA1, cA2 = nA2, cA3 = nA3;
+    const double2 cC0 = nC0, cC1 = nC1, cC2 = nC2, cC3 = nC3;
+    nA0 = Ap[idx + 4]; nA1 = Ap[idx + 5]; nA2 = Ap[idx + 6]; nA3 = Ap[idx + 7];
+    nC0 = ab[idx + 4]; nC1 = ab[idx + 5]; nC2 = ab[idx + 6]; nC3 = ab[idx + 7];
+#define SH_TERM(cA, cC, J)                                                      \
+    {                                                                           \
+      const double tx = (cA) * x;                                               \
+      const double q = fma(tx, q1, -q2);                                        \
+      C = fma((cC).x, q, C); S = fma((cC).y, q, S);                             \
+      q2 = q1; q1 = q;                                                          \
+      if (idx + (J) == bend) {                                                  \
+        r = fma(u, C, r); r = fma(v, S, r);                                     \
+        m++; bend += L + 1 - m;                                                 \
+        const double t1 = v * zy, un = fma(u, zx, -t1);                         \
+        const double t2 = v * zx, vn = fma(u, zy, t2);                          \
+        u = un; v = vn; C = 0.0; S = 0.0; q1 = 0.0; q2 = -1.0;                  \
+      }                                                                         \
+    }
+    SH_TERM(cA0, cC0, 0) SH_TERM(cA1, cC1, 1) SH_TERM(cA2, cC2, 2) SH_TERM(cA3, cC3, 3)
+#undef SH_TERM
+  }
+  rho_out = rho;
+  return r;
+}
+
+
+
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
 
 template <int ILP>
