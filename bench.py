@@ -32,7 +32,7 @@ sys.path.insert(0, ROOT)
 
 import shpkg  # noqa: E402
 
-EVAL_DRAM_BYTES_PER_RECORD = 36.6   # measured, see the roofline.traffic note below
+EVAL_DRAM_BYTES_PER_RECORD = 33.2   # measured, see the roofline.traffic note below
 METRIC = "contact_pair_evals_per_s"
 UNIT = "pair-evals/s"
 
