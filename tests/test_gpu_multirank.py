@@ -21,13 +21,14 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 rank, world = dist.get_rank(), dist.get_world_size()
 cfg = W.packing((6, 4, 4), 20, (32, 64), nshapes=4, seed=21, periodic=True, name="mr", skin=0.03, vel_sigma=0.5, dt=4e-4)
 nsteps = 300
-dd = D.DomainDecomposition(pkg.ShGpu(device=local), cfg, comm_device="cuda")
+eng = pkg.ShGpu(device=local); eng.set_pair_tuning(0, 0, 16)   # force the split pipeline + candidate cache with ghosts
+dd = D.DomainDecomposition(eng, cfg, comm_device="cuda")
 dd.setup()
 f0 = dd.gather_owned(("f", "torque"))
 nreb = dd.run(nsteps)
 got = dd.gather_owned(("x", "v", "quat", "angmom", "f"))
 if rank == 0:
-    g = pkg.ShGpu(device=local); W.apply(g, cfg); g.compute_forces(); r0 = g.get_atoms()
+    g = pkg.ShGpu(device=local); W.apply(g, cfg); g.set_pair_tuning(0, 0, 16); g.compute_forces(); r0 = g.get_atoms()
     fs = np.abs(r0["f"]).max()
     assert np.abs(f0["f"] - r0["f"]).max() <= 1e-11 * fs, np.abs(f0["f"] - r0["f"]).max() / fs
     assert np.abs(f0["torque"] - r0["torque"]).max() <= 1e-11 * fs

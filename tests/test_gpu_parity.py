@@ -18,11 +18,17 @@ TOL = 1e-10
 pytestmark = pytest.mark.gpu
 
 
-def both(cfg, threads=8):
+# pair-phase pipelines every physics test runs through: 0 = default (fused kernel below 16384 pairs, split
+# cull/evaluate/reduce pipeline above), 16 = split pipeline forced (with direction-cell bound and candidate cache)
+PIPELINES = [0, 16]
+
+
+def both(cfg, threads=8, variant=0):
     g = pkg.ShGpu()
     o = O.Oracle(threads=threads)
     W.apply(g, cfg)
     W.apply(o, cfg)
+    g.set_pair_tuning(0, 0, variant)
     return g, o
 
 
@@ -56,8 +62,9 @@ def test_shape_tables_bit_identical():
         assert np.array_equal(ng[0], no[0]) and np.array_equal(ng[1], no[1])
 
 
+@pytest.mark.parametrize("variant", PIPELINES)
 @pytest.mark.parametrize("exponent", [1.0, 1.5])
-def test_two_particle_sweep(exponent):
+def test_two_particle_sweep(exponent, variant):
     """configs[0]: two SH ellipsoids (l_max=20, 32x64), sweep of separations and orientations."""
     rng = np.random.default_rng(7)
     worst = dict(V=0, F=0, tau=0)
@@ -68,7 +75,7 @@ def test_two_particle_sweep(exponent):
         dirv = rng.normal(size=3)
         dirv /= np.linalg.norm(dirv)
         cfg["x"] = np.array([-0.5 * sep * dirv, 0.5 * sep * dirv])
-        g, o = both(cfg, threads=1)
+        g, o = both(cfg, threads=1, variant=variant)
         e = check_forces(g, o)
         ncontact += e["ncontact"]
         for k in worst:
@@ -78,26 +85,29 @@ def test_two_particle_sweep(exponent):
     print("two-particle sweep worst rel err", worst, "contacts", ncontact)
 
 
-def test_packing_all_pairs_l30():
+@pytest.mark.parametrize("variant", PIPELINES)
+def test_packing_all_pairs_l30(variant):
     """Every pair of a periodic 8-shape l_max=30 packing snapshot (configs[2] at reduced size)."""
     cfg = W.config3_packing(500, lmax=30, grid=(48, 96))
-    g, o = both(cfg)
+    g, o = both(cfg, variant=variant)
     e = check_forces(g, o)
     assert e["ncontact"] > 100
     print("packing l30:", e)
 
 
-def test_packing_mixed_lmax_nonperiodic():
+@pytest.mark.parametrize("variant", PIPELINES)
+def test_packing_nonperiodic(variant):
     cfg = W.packing((3, 3, 3), 20, (32, 64), nshapes=3, seed=5, periodic=False, name="np")
-    g, o = both(cfg)
+    g, o = both(cfg, variant=variant)
     e = check_forces(g, o)
     assert e["ncontact"] > 10
 
 
-def test_wall_and_gravity_forces():
+@pytest.mark.parametrize("variant", PIPELINES)
+def test_wall_and_gravity_forces(variant):
     cfg = W.config2_wall(n_side=4)
     cfg["x"] = cfg["x"] - np.array([0, 0, 0.6])  # push the bottom layer into the wall
-    g, o = both(cfg)
+    g, o = both(cfg, variant=variant)
     check_forces(g, o)
     ag, ao = g.get_atoms(), o.get_atoms()
     assert np.abs(ao["f"][:, 2]).max() > 0
@@ -105,12 +115,13 @@ def test_wall_and_gravity_forces():
     assert abs(eg["e_contact"] - eo["e_contact"]) <= 1e-10 * abs(eo["e_contact"])
 
 
-def test_trajectory_two_particle_1000_steps():
+@pytest.mark.parametrize("variant", PIPELINES)
+def test_trajectory_two_particle_1000_steps(variant):
     """configs[0] head-on collision, 1000+ steps: GPU trajectory vs oracle trajectory."""
     cfg = W.config1_two_particle(seed=1)
     cfg["x"] = np.array([[-1.0, 0.05, 0], [1.0, -0.05, 0.02]])
     cfg["dt"] = 5e-4
-    g, o = both(cfg, threads=1)
+    g, o = both(cfg, threads=1, variant=variant)
     g.run(1200); o.run(1200)
     ag, ao = g.get_atoms(), o.get_atoms()
     assert np.abs(ao["angmom"]).max() > 1e-6, "collision did not happen"
@@ -121,21 +132,23 @@ def test_trajectory_two_particle_1000_steps():
         assert abs(eg[k] - eo[k]) <= 1e-8 * max(1.0, abs(eo[k])), k
 
 
-def test_trajectory_small_packing():
+@pytest.mark.parametrize("variant", PIPELINES)
+def test_trajectory_small_packing(variant):
     cfg = W.packing((2, 2, 2), 20, (32, 64), nshapes=2, seed=11, name="traj")
     cfg["box"] = (np.zeros(3), cfg["box"][1] * 1.0, (1, 1, 1))
-    g, o = both(cfg)
+    g, o = both(cfg, variant=variant)
     g.run(1000); o.run(1000)
     ag, ao = g.get_atoms(), o.get_atoms()
     for k, tol in (("x", 1e-8), ("v", 1e-7), ("quat", 1e-8), ("angmom", 1e-7)):
         assert np.abs(ag[k] - ao[k]).max() <= tol * max(1.0, np.abs(ao[k]).max()), k
 
 
-def test_deterministic_bitwise():
+@pytest.mark.parametrize("variant", PIPELINES)
+def test_deterministic_bitwise(variant):
     cfg = W.config3_packing(256, lmax=20, grid=(32, 64))
     outs = []
     for _ in range(2):
-        g = pkg.ShGpu(); W.apply(g, cfg); g.run(20)
+        g = pkg.ShGpu(); W.apply(g, cfg); g.set_pair_tuning(0, 0, variant); g.run(20)
         outs.append(g.get_atoms()); g.close()
     for k in outs[0]:
         assert np.array_equal(outs[0][k], outs[1][k]), k
@@ -182,11 +195,12 @@ def test_deep_overlap_and_poles():
         g.close(); o.close()
 
 
-def test_lmax50_tables_in_global_memory():
+@pytest.mark.parametrize("variant", PIPELINES)
+def test_lmax50_tables_in_global_memory(variant):
     """configs[4] at reduced size: l_max=50, 80x160 quadrature, 8 shapes -> 255 KB of folded tables do not
     fit in shared memory, the pair kernel reads them through L1/L2 instead (SMEM_TABLES=false path)."""
     cfg = W.packing((2, 2, 2), 50, (80, 160), nshapes=8, seed=50, nn_frac=1.8, name="l50")
-    g, o = both(cfg, threads=16)
+    g, o = both(cfg, threads=16, variant=variant)
     e = check_forces(g, o)
     assert e["ncontact"] > 10
     print("l50:", e)
