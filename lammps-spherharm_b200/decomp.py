@@ -235,9 +235,11 @@ class DomainDecomposition:
         rec = np.empty((nl, NREC))
         rec[:, 0] = self.tag; rec[:, 1] = self.shape; rec[:, 2:5] = x; rec[:, 5:8] = st["v"][:nl]
         rec[:, 8:12] = st["quat"][:nl]; rec[:, 12:15] = st["angmom"][:nl]
-        rows_by_dest = [rec[owner == r] for r in range(self.world)]
+        # atoms that stay never touch the transport: only the migrants are exchanged
+        stay = owner == self.rank
+        rows_by_dest = [rec[owner == r] if r != self.rank else rec[:0] for r in range(self.world)]
         got, _, _ = self._alltoall_rows(rows_by_dest, NREC)
-        mine = np.concatenate(got, axis=0)
+        mine = np.concatenate([rec[stay]] + got, axis=0)
         order = np.argsort(mine[:, 0], kind="stable")          # deterministic local order: by tag
         mine = mine[order]
         self.tag = mine[:, 0].astype(np.int64)
