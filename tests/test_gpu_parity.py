@@ -253,6 +253,25 @@ def test_candidate_cache_matches_window_path_over_a_run():
         assert np.abs(a0[k] - a1[k]).max() <= 1e-9 * max(1.0, np.abs(a1[k]).max()), k
 
 
+@pytest.mark.parametrize("variant", PIPELINES)
+def test_odd_quadrature_grid_and_tiny_systems(variant):
+    """Quadrature sizes that are not multiples of the warp size, a single atom, and atoms far apart."""
+    cfg = W.packing((2, 2, 2), 10, (9, 20), nshapes=2, seed=8, nn_frac=1.6, name="odd")
+    g, o = both(cfg, variant=variant)
+    e = check_forces(g, o)
+    assert e["ncontact"] > 5
+    g.close(); o.close()
+    a, b = W.ellipsoid_shape(8)
+    for xs in ([[0.0, 0, 0]], [[0.0, 0, 0], [50.0, 0, 0], [0, 70.0, 0]]):
+        g = pkg.ShGpu(); g.set_quadrature(9, 20); g.add_shape(8, a, b); g.set_pair_tuning(0, 0, variant)
+        g.set_atoms(np.zeros(len(xs), np.int32), np.array(xs), v=np.ones((len(xs), 3)))
+        g.run(10)
+        at = g.get_atoms()
+        assert np.allclose(at["x"], np.array(xs) + 10 * 1e-4) and np.all(at["f"] == 0)
+        assert g.get_pairs()["V"].size == 0
+        g.close()
+
+
 def test_error_paths():
     g = pkg.ShGpu()
     with pytest.raises(pkg.ShGpuError):
