@@ -87,6 +87,11 @@ int sh_put_state(sh_ctx *h, int64_t n, const double *x, const double *v, const d
                  const double *angmom);
 int sh_get_forces(const sh_ctx *h, int64_t n, double *f, double *torque);
 
+/* write_restart / read_restart (AtomVec::pack_restart): binary snapshot of the owned atoms (tag, shape, x, v, quat,
+ * angmom) and the box.  Shapes / coefficients / fixes are re-issued by the caller before reading, as in LAMMPS. */
+int sh_write_snapshot(const sh_ctx *h, const char *path, int64_t step);
+int sh_read_snapshot(sh_ctx *h, const char *path, int64_t *step_out);
+
 /* state read-back (dump / thermo / compute) ---------------------------------------------------- */
 int sh_get_natoms(const sh_ctx *h, int64_t *n);
 int sh_get_atoms(const sh_ctx *h, int64_t n, double *x, double *v, double *quat, double *angmom,

@@ -199,6 +199,16 @@ class ShGpu:
         self._ck(self.L.sh_get_run_time(self.h, C.byref(a), C.byref(b)))
         return dict(last=a.value, total=b.value)
 
+    def write_snapshot(self, path, step=0):
+        self._ck(self.L.sh_write_snapshot(self.h, str(path).encode(), C.c_int64(step)))
+
+    def read_snapshot(self, path):
+        step, n = C.c_int64(0), C.c_int64(0)
+        self._ck(self.L.sh_read_snapshot(self.h, str(path).encode(), C.byref(step)))
+        self.L.sh_get_natoms(self.h, C.byref(n))
+        self.n = n.value
+        return step.value
+
     # ---- read-back ---------------------------------------------------------------------------
     def get_atoms(self, fields=("x", "v", "quat", "angmom", "f", "torque")):
         n = self.n

@@ -951,6 +951,55 @@ int sh_get_forces(const sh_ctx *hc, int64_t n, double *f, double *torque) {
   return 0;
 }
 
+// ---- checkpoint / resume (write_restart / read_restart of the atom style: AtomVec::pack_restart): binary
+// snapshot of the owned atoms.  Shapes, coefficients and fixes are re-issued by the input script, as in LAMMPS.
+namespace {
+struct SnapHeader { char magic[8]; int32_t version, nshapes; int64_t n, step; double lo[3], hi[3]; int32_t periodic[3], pad; };
+}
+int sh_write_snapshot(const sh_ctx *hc, const char *path, int64_t step) {
+  sh_ctx *h = const_cast<sh_ctx *>(hc);
+  const int64_t n = h->n - h->nghost;
+  std::vector<double> x(3 * n), v(3 * n), q(4 * n), L(3 * n);
+  if (n > 0) { int rc = sh_get_atoms(h, n, x.data(), v.data(), q.data(), L.data(), nullptr, nullptr); if (rc) return rc; }
+  std::vector<int> shp(h->stride > 0 ? h->stride : 1);
+  if (n > 0) CU(cudaMemcpy(shp.data(), h->shape.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+  FILE *f = fopen(path, "wb");
+  if (!f) return fail(h, std::string("cannot open snapshot file ") + path);
+  SnapHeader hd{};
+  std::memcpy(hd.magic, "SHGPUSNP", 8);
+  hd.version = 1; hd.nshapes = (int)h->shapes.size(); hd.n = n; hd.step = step;
+  for (int d = 0; d < 3; d++) { hd.lo[d] = h->lo[d]; hd.hi[d] = h->hi[d]; hd.periodic[d] = h->periodic[d]; }
+  bool ok = fwrite(&hd, sizeof hd, 1, f) == 1;
+  ok = ok && (n == 0 || (fwrite(h->tag.data(), sizeof(int64_t), n, f) == (size_t)n && fwrite(shp.data(), sizeof(int), n, f) == (size_t)n &&
+                         fwrite(x.data(), 8, 3 * n, f) == (size_t)(3 * n) && fwrite(v.data(), 8, 3 * n, f) == (size_t)(3 * n) &&
+                         fwrite(q.data(), 8, 4 * n, f) == (size_t)(4 * n) && fwrite(L.data(), 8, 3 * n, f) == (size_t)(3 * n)));
+  fclose(f);
+  if (!ok) return fail(h, "short write to snapshot file");
+  return 0;
+}
+int sh_read_snapshot(sh_ctx *h, const char *path, int64_t *step_out) {
+  FILE *f = fopen(path, "rb");
+  if (!f) return fail(h, std::string("cannot open snapshot file ") + path);
+  SnapHeader hd{};
+  if (fread(&hd, sizeof hd, 1, f) != 1 || std::memcmp(hd.magic, "SHGPUSNP", 8) != 0 || hd.version != 1) { fclose(f); return fail(h, "not a shgpu snapshot (bad header)"); }
+  if (hd.nshapes != (int)h->shapes.size()) { fclose(f); return fail(h, "snapshot was written with a different number of shapes"); }
+  const int64_t n = hd.n;
+  if (n < 0 || n > ((int64_t)1 << 30)) { fclose(f); return fail(h, "bad atom count in snapshot"); }
+  std::vector<int64_t> tag(n); std::vector<int> shp(n);
+  std::vector<double> x(3 * n), v(3 * n), q(4 * n), L(3 * n);
+  bool ok = n == 0 || (fread(tag.data(), sizeof(int64_t), n, f) == (size_t)n && fread(shp.data(), sizeof(int), n, f) == (size_t)n &&
+                       fread(x.data(), 8, 3 * n, f) == (size_t)(3 * n) && fread(v.data(), 8, 3 * n, f) == (size_t)(3 * n) &&
+                       fread(q.data(), 8, 4 * n, f) == (size_t)(4 * n) && fread(L.data(), 8, 3 * n, f) == (size_t)(3 * n));
+  fclose(f);
+  if (!ok) return fail(h, "truncated snapshot file");
+  int rc = sh_set_box(h, hd.lo, hd.hi, hd.periodic);
+  if (rc) return rc;
+  rc = sh_set_atoms(h, n, tag.data(), shp.data(), x.data(), v.data(), q.data(), L.data());
+  if (rc) return rc;
+  if (step_out) *step_out = hd.step;
+  return 0;
+}
+
 int sh_get_natoms(const sh_ctx *h, int64_t *n) { if (n) *n = h->n; return 0; }
 
 int sh_get_atoms(const sh_ctx *hc, int64_t n, double *x, double *v, double *quat, double *angmom, double *f, double *torque) {

@@ -12,7 +12,7 @@
 // vx vy vz ; velocity <id> set ... ; pair_style spherharm ; pair_coeff i j k exponent ; fix <id> <grp>
 // nve/sh | wall/spherharm <xplane|yplane|zplane> <pos> <k> <exponent> [hi] | gravity <g> vector x y z |
 // viscous <gamma> ; neighbor <skin> bin ; neigh_modify every N [check yes|no] ; timestep ; thermo N ;
-// dump <id> <grp> custom N <file> ... ; run N ; print "..."
+// dump <id> <grp> custom N <file> ... ; run N ; write_restart <file> ; read_restart <file> ; print "..."
 //
 // Shape file: text rows `l m a_lm b_lm` (real orthonormal SH, no Condon-Shortley phase; missing rows = 0).
 // Data file: LAMMPS-style header (`N atoms`, `T atom types`, `xlo xhi` ...) and an `Atoms` section with
@@ -99,6 +99,7 @@ struct Shlmp {
   int every = 1, check = 1, thermo = 0;
   int64_t step = 0;
   std::vector<Dump> dumps;
+  std::string restart_file;
 
   void ck(int rc) { if (rc != 0) error_all(FLERR, sh_last_error(h)); }
 
@@ -107,6 +108,7 @@ struct Shlmp {
     if (initialised) return;
     if (avec.lmax < 0) error_all(FLERR, "atom_style spherharm is required");
     if (!box_defined) error_all(FLERR, "Box must be defined before run");
+    if (!restart_file.empty() && avec.nlocal() > 0) error_all(FLERR, "read_restart cannot be combined with create_atoms / read_data");
     if (!pair_defined) error_all(FLERR, "pair_style spherharm is required");
     ck(sh_set_box(h, lo, hi, periodic));
     ck(sh_set_quadrature(h, avec.n_theta, avec.n_phi));
@@ -121,7 +123,16 @@ struct Shlmp {
       if (avec.type[i] < 1 || avec.type[i] > (int)avec.shape_files.size()) error_all(FLERR, "Invalid atom type");
       shape[i] = avec.type[i] - 1;
     }
-    ck(sh_set_atoms(h, (int64_t)avec.nlocal(), avec.tag.data(), shape.data(), avec.x.data(), avec.v.data(), avec.quat.data(), avec.angmom.data()));
+    if (restart_file.empty()) {
+      ck(sh_set_atoms(h, (int64_t)avec.nlocal(), avec.tag.data(), shape.data(), avec.x.data(), avec.v.data(), avec.quat.data(), avec.angmom.data()));
+    } else {   // read_restart: atoms, box and step come from the snapshot
+      int64_t st = 0, n = 0;
+      ck(sh_read_snapshot(h, restart_file.c_str(), &st));
+      step = st;
+      ck(sh_get_natoms(h, &n));
+      avec.tag.resize(n); avec.type.assign(n, 1); avec.x.resize(3 * n); avec.v.resize(3 * n); avec.quat.resize(4 * n); avec.angmom.resize(3 * n);
+      for (int64_t i = 0; i < n; i++) avec.tag[i] = i + 1;
+    }
     for (auto &c : coeffs) ck(sh_pair_coeff(h, c.i - 1, c.j - 1, c.k, c.e));
     for (auto &w : walls) ck(sh_add_wall(h, w.p, w.n, w.k, w.e));
     ck(sh_set_gravity(h, g));
@@ -299,6 +310,13 @@ void execute(Shlmp &S, const std::vector<std::string> &t) {
   if (c == "thermo") { need(2); S.thermo = std::stoi(t[1]); return; }
   if (c == "dump") { need(6); Dump d; d.every = std::stoi(t[4]); d.file = t[5]; S.dumps.push_back(d); return; }
   if (c == "run") { need(2); S.run(std::stoll(t[1])); return; }
+  if (c == "write_restart") { need(2); S.init(); S.ck(sh_write_snapshot(S.h, t[1].c_str(), S.step)); return; }
+  if (c == "read_restart") {   // atoms + box from a snapshot; atom_style (shapes) must already be defined
+    need(2);
+    if (S.avec.lmax < 0) error_all(FLERR, "atom_style spherharm must be defined before read_restart");
+    S.restart_file = t[1]; S.box_defined = true;
+    return;
+  }
   if (c == "print") { need(2); printf("%s\n", t[1].c_str()); return; }
   error_all(FLERR, "Unknown command: " + c);
 }

@@ -272,6 +272,28 @@ def test_odd_quadrature_grid_and_tiny_systems(variant):
         g.close()
 
 
+def test_snapshot_restart_roundtrip(tmp_path):
+    """write_restart / read_restart: a run resumed from a snapshot continues like the uninterrupted run."""
+    cfg = W.packing((3, 3, 3), 12, (16, 32), nshapes=3, seed=23, nn_frac=1.75, vel_sigma=0.4, dt=3e-4, name="snap")
+    g = pkg.ShGpu(); W.apply(g, cfg); g.run(60)
+    snap = tmp_path / "state.shsnap"
+    g.write_snapshot(snap, step=60)
+    g.run(60)
+    ref = g.get_atoms(); g.close()
+    g2 = pkg.ShGpu(); W.apply(g2, cfg)           # shapes / coefficients / fixes re-issued, atoms replaced by the snapshot
+    assert g2.read_snapshot(snap) == 60
+    g2.run(60)
+    got = g2.get_atoms(); g2.close()
+    for k in ("x", "v", "quat", "angmom"):
+        assert np.abs(got[k] - ref[k]).max() <= 1e-11 * max(1.0, np.abs(ref[k]).max()), k
+    g3 = pkg.ShGpu()
+    with pytest.raises(pkg.ShGpuError):
+        g3.read_snapshot(snap)                    # no shapes defined: refused
+    bad = tmp_path / "bad.shsnap"; bad.write_bytes(b"not a snapshot")
+    with pytest.raises(pkg.ShGpuError):
+        g3.read_snapshot(bad)
+
+
 def test_error_paths():
     g = pkg.ShGpu()
     with pytest.raises(pkg.ShGpuError):
