@@ -86,6 +86,7 @@ struct Dump { std::string file; int every = 0; };
 
 struct Shlmp {
   sh_ctx *h = nullptr;
+  bool dry = false;     // -check: parse and validate the script (files, arguments, command order) without a device
   AtomVecSpherharm avec;
   bool box_defined = false, initialised = false, pair_defined = false, nve_defined = false;
   double lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
@@ -108,6 +109,14 @@ struct Shlmp {
     if (initialised) return;
     if (avec.lmax < 0) error_all(FLERR, "atom_style spherharm is required");
     if (!box_defined) error_all(FLERR, "Box must be defined before run");
+    if (dry) {
+      if (!pair_defined) error_all(FLERR, "pair_style spherharm is required");
+      for (auto &fn : avec.shape_files) { std::vector<double> a, b; read_shape_file(fn, avec.lmax, a, b); }
+      for (size_t i = 0; i < avec.nlocal(); i++)
+        if (avec.type[i] < 1 || avec.type[i] > (int)avec.shape_files.size()) error_all(FLERR, "Invalid atom type");
+      initialised = true;
+      return;
+    }
     if (!restart_file.empty() && avec.nlocal() > 0) error_all(FLERR, "read_restart cannot be combined with create_atoms / read_data");
     if (!pair_defined) error_all(FLERR, "pair_style spherharm is required");
     ck(sh_set_box(h, lo, hi, periodic));
@@ -169,6 +178,7 @@ struct Shlmp {
     }
   }
   void run(int64_t nsteps) {
+    if (dry) { init(); printf("check: run %lld with %zu atoms, %zu shape(s), %zu wall(s) OK\n", (long long)nsteps, avec.nlocal(), avec.shape_files.size(), walls.size()); step += nsteps; return; }
     if (!nve_defined) fprintf(stderr, "WARNING: no fix nve/sh defined; atoms are integrated by the device step anyway\n");
     init();
     ck(sh_compute_forces(h));
@@ -306,11 +316,11 @@ void execute(Shlmp &S, const std::vector<std::string> &t) {
   }
   if (c == "neighbor") { need(2); S.skin = std::stod(t[1]); return; }
   if (c == "neigh_modify") { for (size_t k = 1; k + 1 < t.size(); k += 2) { if (t[k] == "every") S.every = std::stoi(t[k + 1]); else if (t[k] == "check") S.check = t[k + 1] == "yes"; } return; }
-  if (c == "timestep") { need(2); S.dt = std::stod(t[1]); if (S.initialised) S.ck(sh_set_timestep(S.h, S.dt)); return; }
+  if (c == "timestep") { need(2); S.dt = std::stod(t[1]); if (!(S.dt > 0)) error_all(FLERR, "Illegal timestep command"); if (S.initialised && !S.dry) S.ck(sh_set_timestep(S.h, S.dt)); return; }
   if (c == "thermo") { need(2); S.thermo = std::stoi(t[1]); return; }
   if (c == "dump") { need(6); Dump d; d.every = std::stoi(t[4]); d.file = t[5]; S.dumps.push_back(d); return; }
   if (c == "run") { need(2); S.run(std::stoll(t[1])); return; }
-  if (c == "write_restart") { need(2); S.init(); S.ck(sh_write_snapshot(S.h, t[1].c_str(), S.step)); return; }
+  if (c == "write_restart") { need(2); S.init(); if (!S.dry) S.ck(sh_write_snapshot(S.h, t[1].c_str(), S.step)); return; }
   if (c == "read_restart") {   // atoms + box from a snapshot; atom_style (shapes) must already be defined
     need(2);
     if (S.avec.lmax < 0) error_all(FLERR, "atom_style spherharm must be defined before read_restart");
@@ -324,16 +334,18 @@ void execute(Shlmp &S, const std::vector<std::string> &t) {
 }  // namespace
 
 int main(int argc, char **argv) {
-  std::string infile; int device = 0;
+  std::string infile; int device = 0; bool check_only = false;
   for (int k = 1; k < argc; k++) {
     std::string a = argv[k];
     if ((a == "-in" || a == "-i") && k + 1 < argc) infile = argv[++k];
     else if (a == "-device" && k + 1 < argc) device = std::atoi(argv[++k]);
-    else if (a == "-h" || a == "--help") { printf("usage: shlmp -in <input script> [-device N]\n"); return 0; }
+    else if (a == "-check") check_only = true;
+    else if (a == "-h" || a == "--help") { printf("usage: shlmp -in <input script> [-device N] [-check]\n"); return 0; }
   }
   Shlmp S;
+  S.dry = check_only;
   try {
-    if (sh_create(&S.h, device) != 0) { fprintf(stderr, "ERROR: no usable CUDA device (libshgpu has no CPU fallback)\n"); return 1; }
+    if (!check_only && sh_create(&S.h, device) != 0) { fprintf(stderr, "ERROR: no usable CUDA device (libshgpu has no CPU fallback)\n"); return 1; }
     std::ifstream fin; std::istream *in = &std::cin;
     if (!infile.empty()) { fin.open(infile); if (!fin) { fprintf(stderr, "ERROR: Cannot open input script %s\n", infile.c_str()); return 1; } in = &fin; }
     printf("shlmp (SPHERHARM on libshgpu %d)\n", sh_version());
@@ -354,6 +366,6 @@ int main(int argc, char **argv) {
     if (S.h) sh_destroy(S.h);
     return 1;
   }
-  sh_destroy(S.h);
+  if (S.h) sh_destroy(S.h);
   return 0;
 }
