@@ -1,0 +1,70 @@
+"""Full-size GPU parity (BASELINE configs[2] at bench size: 96,000 particles, 8 shapes, l_max=30, 48x96, the
+relaxed jammed packing bench.py times): direct comparison of every pair with the CPU oracle, and size-independent
+properties (momentum balance, periodic-replica equality, pipeline agreement, bitwise determinism)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_py as O
+import shpkg
+from helpers import pair_rel_errors
+
+pkg = shpkg.load()
+W = pkg.workloads
+pytestmark = pytest.mark.gpu
+REPS = (4, 3, 2)
+
+
+@pytest.fixture(scope="module")
+def full():
+    cfg = W.tiled_packing(REPS, vel_sigma=0.0)
+    g = pkg.ShGpu(); W.apply(g, cfg); g.compute_forces()
+    return cfg, g
+
+
+def test_every_pair_matches_the_oracle_at_full_size(full):
+    cfg, g = full
+    o = O.Oracle(threads=os.cpu_count() or 1)
+    W.apply(o, cfg)
+    o.compute_forces()
+    cg, co = g.get_counters(), o.get_counters()
+    assert cg["pair_evals"] == co["pair_evals"] > 500000
+    assert cg["nodes_inside"] == co["nodes_inside"] > 100000          # every node decision identical
+    assert cg["nodes_evaluated"] < 0.2 * co["nodes_evaluated"]       # ... with < 20 % of the oracle's series evaluations
+    e = pair_rel_errors(g.get_pairs(), o.get_pairs())
+    assert e["ncontact"] > 50000 and max(e["V"], e["F"], e["tau"], e["centroid"]) <= 1e-10, e
+    fs = np.abs(o.get_atoms()["f"]).max()
+    assert np.abs(g.get_atoms()["f"] - o.get_atoms()["f"]).max() <= 1e-10 * fs
+    ge, oe = g.get_energy(), o.get_energy()
+    assert abs(ge["e_contact"] - oe["e_contact"]) <= 1e-11 * oe["e_contact"]
+    o.close()
+
+
+def test_momentum_balance_and_replica_equality(full):
+    cfg, g = full
+    at = g.get_atoms(("f", "torque"))
+    f = at["f"]
+    assert np.abs(f.sum(0)).max() <= 1e-11 * np.abs(f).sum()             # pair forces are exactly antisymmetric
+    n0 = 4000
+    tiles = f.reshape(-1, n0, 3)
+    scale = np.abs(f).max()
+    assert np.abs(tiles - tiles[0]).max() <= 1e-9 * scale                  # periodic replicas feel the same forces
+    tq = at["torque"].reshape(-1, n0, 3)
+    assert np.abs(tq - tq[0]).max() <= 1e-9 * scale
+
+
+def test_pipelines_agree_and_runs_are_bitwise_reproducible(full):
+    cfg, g = full
+    base = g.get_atoms(("f", "torque"))
+    cin = g.get_counters()["nodes_inside"]
+    for variant in (4, 16 | 8):       # fused warp-per-pair kernel; split pipeline without the candidate cache
+        h = pkg.ShGpu(); W.apply(h, cfg); h.set_pair_tuning(0, 0, variant); h.compute_forces()
+        assert h.get_counters()["nodes_inside"] == cin
+        a = h.get_atoms(("f", "torque"))
+        assert np.abs(a["f"] - base["f"]).max() <= 1e-10 * np.abs(base["f"]).max()
+        h.close()
+    h = pkg.ShGpu(); W.apply(h, cfg); h.compute_forces()
+    a = h.get_atoms(("f", "torque"))
+    assert np.array_equal(a["f"], base["f"]) and np.array_equal(a["torque"], base["torque"])
+    h.close()
