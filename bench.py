@@ -32,6 +32,7 @@ sys.path.insert(0, ROOT)
 
 import shpkg  # noqa: E402
 
+CULL_DRAM_BYTES_PER_PAIR = 966.0    # pair_cull_kernel, ncu capture r01 (profiles/r01_cull_kernel_ncu_summary.txt): 553 MB / 572,376 pairs
 EVAL_DRAM_BYTES_PER_RECORD = 33.2   # measured, see the roofline.traffic note below
 METRIC = "contact_pair_evals_per_s"
 UNIT = "pair-evals/s"
@@ -292,6 +293,15 @@ def run_graft(args):
         phase_achieved = achieved
         achieved = ev_flops / ev_s / 1e12
         kshare = {k: v / max(pair_s, 1e-12) for k, v in st_t.items()}
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+            hbm_src = "MEASURED_PEAKS.json"
+        except Exception:
+            hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+        cull_gbs = CULL_DRAM_BYTES_PER_PAIR * cnt["pair_evals"] / max(st_t["cull"], 1e-12) / 1e9
+        cull_info = {"bound": "latency / instruction issue (FP32 + integer + gathers from L2), not HBM and not FP64",
+                     "hbm_gbs": cull_gbs, "hbm_peak_gbs": hbm_peak, "hbm_frac": cull_gbs / hbm_peak, "hbm_peak_source": hbm_src,
+                     "avg_launch_ms": 1e3 * st_t["cull"] / max(1, tim["pair_launches"])}
         roofline = {"bound": "fp64", "kernel": "pair_eval_kernel", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": achieved / peak_tf,
                     # dram__bytes_read.sum + dram__bytes_write.sum of pair_eval_kernel from one ncu --set full capture
@@ -303,6 +313,7 @@ def run_graft(args):
                     "eval_kernel_flops_per_launch": ev_flops / max(1, tim["pair_launches"]),
                     "pair_phase": {"achieved_tflops": phase_achieved, "frac": phase_achieved / peak_tf,
                                    "kernel_share_of_phase": kshare,
+                                   "cull_kernel": cull_info,
                                    "note": "the phase is dominated by pair_cull_kernel, an instruction/latency-bound FP32+integer "
                                            "kernel (window scan, conservative FP32 pre-cull, exact FP64 test on the candidates)"},
                     "peak_source": "K0 DFMA microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 entry); "
