@@ -18,11 +18,14 @@ import shpkg, oracle_py as O
 pkg = shpkg.load(); W = pkg.workloads; D = pkg.load_decomp()
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
-cfg = W.packing((4, 3, 3), 6, (12, 24), nshapes=3, seed=9, periodic=bool(periodic), name="dd", skin=0.1)
+cells = (5, 5, 5) if world == 8 else (4, 3, 3)      # 2x2x2 bricks: in a periodic box the +1 and -1 neighbours coincide
+cfg = W.packing(cells, 6, (12, 24), nshapes=3, seed=9, periodic=bool(periodic), name="dd", skin=0.1)
 ref = None
 if rank == 0:
     o = O.Oracle(threads=2); W.apply(o, cfg); o.compute_forces(); ref = o.get_atoms()
-dd = D.DomainDecomposition(O.Oracle(threads=2), cfg, comm_device="cpu")
+dd = D.DomainDecomposition(O.Oracle(threads=1 if world == 8 else 2), cfg, comm_device="cpu")
+if world == 8:
+    assert tuple(dd.pgrid) == (2, 2, 2), dd.pgrid
 dd.setup()
 got = dd.gather_owned(("x", "f", "torque"))
 counts = [None] * world
@@ -58,12 +61,12 @@ dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize("world,periodic", [(2, 1), (2, 0), (4, 1)])
+@pytest.mark.parametrize("world,periodic", [(2, 1), (2, 0), (4, 1), (8, 1), (8, 0)])
 def test_decomposed_forces_equal_single_domain(tmp_path, world, periodic):
     w = tmp_path / "worker.py"
     w.write_text(WORKER)
     out = tmp_path / "ok.txt"
-    env = dict(os.environ, OMP_NUM_THREADS="2")
+    env = dict(os.environ, OMP_NUM_THREADS="1" if world == 8 else "2")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(29600 + world * 2 + periodic), str(w), ROOT, str(periodic), str(out)]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
