@@ -129,6 +129,27 @@ class Oracle:
     def run(self, nsteps):
         self._ck(self.L.orc_run(self.h, C.c_int64(nsteps)))
 
+    # ---- multi-rank test support: the surface decomp.py drives (host pointers instead of device pointers)
+    def set_ghost_count(self, nghost):
+        self._ck(self.L.orc_set_ghost_count(self.h, C.c_int64(nghost)))
+
+    def step_begin(self):
+        flag = C.c_int(0)
+        self._ck(self.L.orc_step_begin(self.h, C.byref(flag)))
+        return flag.value
+
+    def step_end(self, rebuild):
+        self._ck(self.L.orc_step_end(self.h, int(rebuild)))
+
+    def synchronize(self):
+        pass
+
+    def pack_atoms(self, m, idx_ptr, shift_ptr, out_ptr):
+        self._ck(self.L.orc_pack_atoms(self.h, C.c_int64(m), C.c_void_p(idx_ptr), C.c_void_p(shift_ptr), C.c_void_p(out_ptr)))
+
+    def unpack_ghosts(self, first, m, in_ptr):
+        self._ck(self.L.orc_unpack_ghosts(self.h, C.c_int64(first), C.c_int64(m), C.c_void_p(in_ptr)))
+
     def get_atoms(self, fields=None):
         n = self.n
         out = dict(x=np.zeros((n, 3)), v=np.zeros((n, 3)), quat=np.zeros((n, 4)), angmom=np.zeros((n, 3)),

@@ -53,6 +53,7 @@ struct orc_ctx {
   int64_t n; int64_t *tag; int *shape;
   double *x, *v, *q, *L, *f, *tq;   /* n*3, n*3, n*4, n*3, n*3, n*3 */
   double *Rs, *c;                   /* pose: n*9, n*3 */
+  int64_t nghost; double *c0;        /* multi-rank: last nghost atoms are ghosts; SH origins at the last set_atoms */
   int64_t npair, cappair; pairres_t *pr;
   int64_t cnt_pairs, cnt_trans, cnt_eval, cnt_inside;
   double e_contact; int forces_valid;
@@ -75,7 +76,7 @@ void orc_destroy(orc_ctx *c) {
   if (!c) return;
   for (int i = 0; i < c->nshape; i++) free_shape(&c->shp[i]);
   free(c->tag); free(c->shape); free(c->x); free(c->v); free(c->q); free(c->L); free(c->f); free(c->tq);
-  free(c->Rs); free(c->c); free(c->pr); free(c);
+  free(c->Rs); free(c->c); free(c->c0); free(c->pr); free(c);
 }
 const char *orc_last_error(const orc_ctx *c) { return c->err; }
 
@@ -358,13 +359,13 @@ int orc_set_atoms(orc_ctx *c, int64_t n, const int64_t *tag, const int *shape, c
                   const double *v, const double *quat, const double *angmom) {
   if (n < 0) return fail(c, "n < 0");
   for (int64_t i = 0; i < n; i++) if (shape[i] < 0 || shape[i] >= c->nshape) return fail(c, "atom shape id out of range");
-  free(c->tag); free(c->shape); free(c->x); free(c->v); free(c->q); free(c->L); free(c->f); free(c->tq); free(c->Rs); free(c->c);
-  c->n = n;
+  free(c->tag); free(c->shape); free(c->x); free(c->v); free(c->q); free(c->L); free(c->f); free(c->tq); free(c->Rs); free(c->c); free(c->c0);
+  c->n = n; c->nghost = 0;
   size_t m = (size_t)(n > 0 ? n : 1);
   c->tag = (int64_t *)malloc(m * sizeof(int64_t)); c->shape = (int *)malloc(m * sizeof(int));
   c->x = (double *)calloc(m * 3, 8); c->v = (double *)calloc(m * 3, 8); c->q = (double *)calloc(m * 4, 8);
   c->L = (double *)calloc(m * 3, 8); c->f = (double *)calloc(m * 3, 8); c->tq = (double *)calloc(m * 3, 8);
-  c->Rs = (double *)calloc(m * 9, 8); c->c = (double *)calloc(m * 3, 8);
+  c->Rs = (double *)calloc(m * 9, 8); c->c = (double *)calloc(m * 3, 8); c->c0 = (double *)calloc(m * 3, 8);
   for (int64_t i = 0; i < n; i++) {
     c->tag[i] = tag ? tag[i] : i + 1; c->shape[i] = shape[i];
     for (int d = 0; d < 3; d++) { c->x[3 * i + d] = x[3 * i + d]; c->v[3 * i + d] = v ? v[3 * i + d] : 0.0; c->L[3 * i + d] = angmom ? angmom[3 * i + d] : 0.0; }
@@ -448,6 +449,7 @@ static int build_neighbors(orc_ctx *c) {
         double d[3] = {c->c[3 * i] - c->c[3 * j], c->c[3 * i + 1] - c->c[3 * j + 1], c->c[3 * i + 2] - c->c[3 * j + 2]};
         min_image(c, d);
         double rc = c->shp[c->shape[i]].rmax + c->shp[c->shape[j]].rmax + c->skin;
+        if (i >= c->n - c->nghost) continue;   /* ghost-ghost pairs belong to other ranks */
         if (d[0] * d[0] + d[1] * d[1] + d[2] * d[2] < rc * rc) push_pair(c, (int)i, (int)j);
       }
     return 0;
@@ -488,6 +490,7 @@ static int build_neighbors(orc_ctx *c) {
         double d[3] = {c->c[3 * i] - c->c[3 * j], c->c[3 * i + 1] - c->c[3 * j + 1], c->c[3 * i + 2] - c->c[3 * j + 2]};
         min_image(c, d);
         double rc = c->shp[c->shape[i]].rmax + c->shp[c->shape[j]].rmax + c->skin;
+        if (i >= c->n - c->nghost) continue;
         if (d[0] * d[0] + d[1] * d[1] + d[2] * d[2] < rc * rc) push_pair(c, (int)i, j);
       }
     }
@@ -707,6 +710,73 @@ int orc_run(orc_ctx *c, int64_t nsteps) {
         c->L[3 * i + d] = (c->L[3 * i + d] + dth * c->tq[3 * i + d]) * damp_L;
       }
     }
+  }
+  return 0;
+}
+
+/* ---- multi-rank test support: same split step / ghost pack-unpack surface as libshgpu (host pointers) ---- */
+int orc_set_ghost_count(orc_ctx *c, int64_t nghost) {
+  if (nghost < 0 || nghost > c->n) return fail(c, "ghost count out of range");
+  c->nghost = nghost; c->forces_valid = 0;
+  compute_pose(c);
+  memcpy(c->c0, c->c, (size_t)c->n * 24);
+  return 0;
+}
+int orc_step_begin(orc_ctx *c, int *rebuild_wanted) {
+  if (!c->forces_valid) { if (orc_compute_forces(c)) return -1; memcpy(c->c0, c->c, (size_t)c->n * 24); }
+  const int64_t nl = c->n - c->nghost;
+  const double dt = c->dt, dth = 0.5 * dt;
+  const double damp_v = 1.0 - 0.5 * dt * c->gamma_lin, damp_L = 1.0 - 0.5 * dt * c->gamma_rot;
+  for (int64_t i = 0; i < nl; i++) {
+    const shape_t *s = &c->shp[c->shape[i]];
+    double im = 1.0 / s->mass;
+    for (int d = 0; d < 3; d++) {
+      c->v[3 * i + d] = (c->v[3 * i + d] + dth * (c->f[3 * i + d] * im + c->g[d])) * damp_v;
+      c->x[3 * i + d] += dt * c->v[3 * i + d];
+      c->L[3 * i + d] = (c->L[3 * i + d] + dth * c->tq[3 * i + d]) * damp_L;
+    }
+    richardson(&c->q[4 * i], &c->L[3 * i], s->inertia, dth);
+  }
+  compute_pose(c);
+  int flag = 0;
+  const double trig2 = 0.25 * c->skin * c->skin;
+  for (int64_t i = 0; i < nl && !flag; i++) {
+    double d2 = 0;
+    for (int d = 0; d < 3; d++) { double dd = c->c[3 * i + d] - c->c0[3 * i + d]; d2 += dd * dd; }
+    if (d2 > trig2) flag = 1;
+  }
+  if (rebuild_wanted) *rebuild_wanted = flag;
+  return 0;
+}
+int orc_step_end(orc_ctx *c, int rebuild) {
+  if (orc_compute_forces(c)) return -1;
+  if (rebuild) memcpy(c->c0, c->c, (size_t)c->n * 24);
+  const int64_t nl = c->n - c->nghost;
+  const double dt = c->dt, dth = 0.5 * dt;
+  const double damp_v = 1.0 - 0.5 * dt * c->gamma_lin, damp_L = 1.0 - 0.5 * dt * c->gamma_rot;
+  for (int64_t i = 0; i < nl; i++) {
+    const shape_t *s = &c->shp[c->shape[i]];
+    double im = 1.0 / s->mass;
+    for (int d = 0; d < 3; d++) {
+      c->v[3 * i + d] = (c->v[3 * i + d] + dth * (c->f[3 * i + d] * im + c->g[d])) * damp_v;
+      c->L[3 * i + d] = (c->L[3 * i + d] + dth * c->tq[3 * i + d]) * damp_L;
+    }
+  }
+  return 0;
+}
+int orc_pack_atoms(const orc_ctx *c, int64_t m, const int *idx, const double *shift, double *out) {
+  for (int64_t k = 0; k < m; k++) {
+    const int i = idx[k];
+    for (int d = 0; d < 3; d++) out[7 * k + d] = c->x[3 * i + d] + (shift ? shift[3 * k + d] : 0.0);
+    for (int d = 0; d < 4; d++) out[7 * k + 3 + d] = c->q[4 * i + d];
+  }
+  return 0;
+}
+int orc_unpack_ghosts(orc_ctx *c, int64_t first, int64_t m, const double *in) {
+  if (first < 0 || first + m > c->n) return fail(c, "unpack range out of bounds");
+  for (int64_t k = 0; k < m; k++) {
+    for (int d = 0; d < 3; d++) c->x[3 * (first + k) + d] = in[7 * k + d];
+    for (int d = 0; d < 4; d++) c->q[4 * (first + k) + d] = in[7 * k + 3 + d];
   }
   return 0;
 }

@@ -45,6 +45,13 @@ int orc_set_damping(orc_ctx *c, double gamma_lin, double gamma_rot);
 int orc_set_threads(orc_ctx *c, int nthreads);
 int orc_compute_forces(orc_ctx *c);
 int orc_run(orc_ctx *c, int64_t nsteps);
+/* multi-rank test support (mirrors sh_set_ghost_count / sh_step_begin / sh_step_end / sh_pack_atoms /
+ * sh_unpack_ghosts; pointers are HOST pointers) */
+int orc_set_ghost_count(orc_ctx *c, int64_t nghost);
+int orc_step_begin(orc_ctx *c, int *rebuild_wanted);
+int orc_step_end(orc_ctx *c, int rebuild);
+int orc_pack_atoms(const orc_ctx *c, int64_t m, const int *idx, const double *shift, double *out);
+int orc_unpack_ghosts(orc_ctx *c, int64_t first, int64_t m, const double *in);
 int orc_get_atoms(const orc_ctx *c, int64_t n, double *x, double *v, double *quat, double *angmom,
                   double *f, double *torque);
 int orc_get_pairs(const orc_ctx *c, int64_t cap, int64_t *npairs, int64_t *tag_i, int64_t *tag_j,
