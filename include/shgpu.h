@@ -109,7 +109,7 @@ int sh_get_timers(const sh_ctx *h, double *seconds_pair, int64_t *pair_launches,
                   double *seconds_neigh, double *seconds_other);
 int sh_reset_timers(sh_ctx *h);
 /* split pair pipeline: device time of the SH-evaluation kernel, its launches, pairs routed to the fused
- * deep-contact kernel, survivor-pool regrowths, candidate-cache builds */
+ * deep-contact kernel, survivor-pool growths, candidate-cache builds */
 /* raw device counters: 0 pairs, 1 nodes transformed, 2 evaluated, 3 inside, 4 pairs with a ghost, 5 evaluated by
  * pair_eval_kernel (the rest of [2] comes from the fused deep-contact kernel) */
 int sh_get_counter_raw(const sh_ctx *h, int index, int64_t *value);
@@ -117,6 +117,9 @@ int sh_get_split_times(const sh_ctx *h, double *seconds_cull, double *seconds_ev
                        double *seconds_deep);
 int sh_get_split_stats(const sh_ctx *h, double *seconds_eval, int64_t *eval_launches, int64_t *deep_pairs,
                        int64_t *pool_redos, int64_t *cache_builds);
+/* candidate cache of the split pipeline: builds and their device time, margin level in use, pairs that took the
+ * window (slow) path */
+int sh_get_cache_stats(const sh_ctx *h, int64_t *cache_builds, double *seconds_cache, int *level, int64_t *slow_pairs);
 /* device time of sh_run (events on the library's stream bracketing all steps of the call) -------- */
 int sh_get_run_time(const sh_ctx *h, double *seconds_last_run, double *seconds_total);
 
@@ -124,6 +127,13 @@ int sh_get_run_time(const sh_ctx *h, double *seconds_last_run, double *seconds_t
  * bound off, 4 fused warp-per-pair kernel, 8 candidate cache off, 16 force the split pipeline (systems with fewer
  * than 16384 pairs default to the fused kernel) -------------------------------------------------- */
 int sh_set_pair_tuning(sh_ctx *h, int threads_per_cta, int ctas_per_sm, int variant);
+
+/* named knobs (0 = default): "cull_wpb" warps per CTA of the cached cull kernel (1, 2, 4, 8; default 1); "cull_lpp"
+ * lanes per pair in that kernel (16, 32; default 16); "eval_pts" points per lane of pair_eval_kernel (2, 4; default 4);
+ * "eval_occ" its minimum CTAs per SM at 2 points (3, 4); "eval_mode" 1 = one block per CTA (default), 2 = persistent
+ * chunks; "cache_level" margin level of the candidate cache (-1 adaptive (default), 0..2 = 0.5 / 1 / 2 % of rmax);
+ * "cube_n" direction cells per cube-face edge of the per-shape bound tables (8..144, default 144; before sh_add_shape) */
+int sh_set_tuning(sh_ctx *h, const char *key, double value);
 
 /* FP64 FMA-pipe peak microbenchmark (K0): returns measured DFMA flop/s of the device ----------- */
 int sh_measure_fp64_peak(sh_ctx *h, double *flops_per_s, double *sm_clock_mhz_est);

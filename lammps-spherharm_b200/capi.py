@@ -263,8 +263,17 @@ class ShGpu:
     def get_split_stats(self):
         a, b, c, d, e = C.c_double(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
         self._ck(self.L.sh_get_split_stats(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(e)))
-        return dict(seconds_eval=a.value, eval_launches=b.value, deep_pairs=c.value, pool_redos=d.value,
+        return dict(seconds_eval=a.value, eval_launches=b.value, deep_pairs=c.value, pool_grows=d.value,
                     cache_builds=e.value)
+
+    def get_cache_stats(self):
+        nb, sec, lv, slow = C.c_int64(), C.c_double(), C.c_int(), C.c_int64()
+        self._ck(self.L.sh_get_cache_stats(self.h, C.byref(nb), C.byref(sec), C.byref(lv), C.byref(slow)))
+        return dict(cache_builds=nb.value, seconds_cache=sec.value, level=lv.value, slow_pairs=slow.value)
+
+    def set_tuning(self, key, value):
+        """Named knobs (include/shgpu.h sh_set_tuning): cull_wpb, eval_pts, cache_level, cube_n."""
+        self._ck(self.L.sh_set_tuning(self.h, str(key).encode(), C.c_double(value)))
 
     def reset_timers(self):
         self._ck(self.L.sh_reset_timers(self.h))

@@ -24,11 +24,11 @@ struct DevShape {
   int tab_off;                            // offset (in records) of this shape in the concatenated table
   int nterms4;                            // nterms rounded up to a multiple of 4; tables hold nterms4+4 records
   const float *row_x;                     // cos(theta_row), float copy for the conservative window
-  const float *cube_b2;                   // conservative r^2 upper bound per cube-map direction cell (6*cube_n^2)
-  int cube_n, pad2_;
-  const float *pf;                        // FP32 copy of the node points (3 x nq, SoA) for the conservative pre-cull
-  const float *cube_w2;                   // candidate-cache table (inflated wide bound^2 per direction cell)
-  double cache_delta;                     // node displacement margin of the candidate cache
+  const float2 *cube_ul;                  // per cube-map direction cell: {ub2, lb2} = proven bounds of r^2 over the cell
+  int cube_n, pad2_;                      // cells per face edge
+  const float4 *pf4;                      // FP32 copy of the node points (x,y,z,0) for the conservative pre-cull
+  const float *cube_w2[3];                // candidate-cache tables per margin level (inflated wide bound^2 per cell)
+  double cache_delta[3];                  // node displacement margin of the candidate cache per level
 };
 
 // rotation matrix (row-major R[3*r+c]) of unit quaternion (w,x,y,z); plain mul/add, fixed order
@@ -128,6 +128,67 @@ __device__ __forceinline__ void sh_radius_folded_x2(int L, const double *__restr
     base += len + 1;
   }
   rhoA = rA; rhoB = rB; rA_out = rrA; rB_out = rrB;
+}
+
+// N points per thread against the same shape (N = 4: one LDS.64 + one LDS.128 per term for 16 FP64 instructions,
+// four independent dependency chains per lane).  Per point the operation sequence is exactly that of
+// sh_radius_folded: results are bit-identical to the one-point evaluation.
+template <int N>
+__device__ __forceinline__ void sh_radius_folded_n(int L, const double *__restrict__ Ap, const double2 *__restrict__ ab,
+                                                   const double (&s)[N][3], const double (&rho2)[N], double (&rho)[N],
+                                                   double (&r_out)[N]) {
+  double x[N], zx[N], zy[N], u[N], v[N], rr[N];
+#pragma unroll
+  for (int p = 0; p < N; p++) {
+    rho[p] = sqrt(rho2[p]);
+    const double inv = 1.0 / rho[p];
+    x[p] = s[p][2] * inv; zx[p] = s[p][0] * inv; zy[p] = s[p][1] * inv;
+    u[p] = 1.0; v[p] = 0.0; rr[p] = 0.0;
+  }
+  int base = 0;
+  for (int m = 0; m <= L; m++) {
+    if (m > 0) {
+#pragma unroll
+      for (int p = 0; p < N; p++) {
+        const double t1 = v[p] * zy[p], un = fma(u[p], zx[p], -t1), t2 = v[p] * zx[p], vn = fma(u[p], zy[p], t2);
+        u[p] = un; v[p] = vn;
+      }
+    }
+    const double2 c0 = ab[base];
+    double C[N], S[N];
+#pragma unroll
+    for (int p = 0; p < N; p++) { C[p] = c0.x; S[p] = c0.y; }
+    const int len = L - m;
+    if (len >= 1) {
+      const double ap1 = Ap[base + 1];
+      const double2 c1 = ab[base + 1];
+      double q1[N], q2[N];
+#pragma unroll
+      for (int p = 0; p < N; p++) {
+        q1[p] = ap1 * x[p]; q2[p] = 1.0;
+        C[p] = fma(c1.x, q1[p], C[p]); S[p] = fma(c1.y, q1[p], S[p]);
+      }
+#pragma unroll 2
+      for (int i = 2; i <= len; i++) {
+        const double ap = Ap[base + i];
+        const double2 ci = ab[base + i];
+        double q[N];
+#pragma unroll
+        for (int p = 0; p < N; p++) { const double tx = ap * x[p]; q[p] = fma(tx, q1[p], -q2[p]); }
+#pragma unroll
+        for (int p = 0; p < N; p++) C[p] = fma(ci.x, q[p], C[p]);
+#pragma unroll
+        for (int p = 0; p < N; p++) S[p] = fma(ci.y, q[p], S[p]);
+#pragma unroll
+        for (int p = 0; p < N; p++) { q2[p] = q1[p]; q1[p] = q[p]; }
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < N; p++) { rr[p] = fma(u[p], C[p], rr[p]); rr[p] = fma(v[p], S[p], rr[p]); }
+    base += len + 1;
+  }
+#pragma unroll
+  for (int p = 0; p < N; p++) r_out[p] = rr[p];
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -147,11 +147,14 @@ __device__ __forceinline__ void for_each_neighbor(const double *c, const int *sh
           const int j = cell_atoms[q];
           if (j == i) continue;
           double d0 = ci0 - c[j], d1 = ci1 - c[stride + j], d2 = ci2 - c[2 * stride + j];
-          if (G.periodic[0]) d0 = d0 - G.boxlen[0] * rint(d0 / G.boxlen[0]);
-          if (G.periodic[1]) d1 = d1 - G.boxlen[1] * rint(d1 / G.boxlen[1]);
-          if (G.periodic[2]) d2 = d2 - G.boxlen[2] * rint(d2 / G.boxlen[2]);
+          // periodic image of the pair: n = rint(d / L) in {-1, 0, 1}, packed 2 bits per dimension (n + 1).  Neighbors are
+          // closer than half a box, so n cannot change before the next build and the pair kernels reuse it.
+          int img = 1 | (1 << 2) | (1 << 4);
+          if (G.periodic[0]) { const double n = rint(d0 / G.boxlen[0]); d0 = d0 - G.boxlen[0] * n; img += (int)n; }
+          if (G.periodic[1]) { const double n = rint(d1 / G.boxlen[1]); d1 = d1 - G.boxlen[1] * n; img += (int)n << 2; }
+          if (G.periodic[2]) { const double n = rint(d2 / G.boxlen[2]); d2 = d2 - G.boxlen[2] * n; img += (int)n << 4; }
           const double rc = ri + shapes[shape[j]].rmax + G.skin;
-          if (d0 * d0 + d1 * d1 + d2 * d2 < rc * rc) fn(j);
+          if (d0 * d0 + d1 * d1 + d2 * d2 < rc * rc) fn(j, img);
         }
       }
 }
@@ -162,31 +165,34 @@ __global__ void nbr_count_kernel(const double *c, const int *shape, const DevSha
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int nf = 0, nh = 0;
-  for_each_neighbor(c, shape, shapes, stride, G, cell_of, cell_start, cell_atoms, i, [&](int j) { nf++; nh += (j > i); });
+  for_each_neighbor(c, shape, shapes, stride, G, cell_of, cell_start, cell_atoms, i, [&](int j, int) { nf++; nh += (j > i); });
   cnt_full[i] = nf;
   cnt_half[i] = nh;
 }
 __global__ void nbr_fill_kernel(const double *c, const int *shape, const DevShape *shapes, int n, int stride,
                                 BinGrid G, const int *cell_of, const int *cell_start, const int *cell_atoms,
                                 const int *nbr_off, const int *half_off, int *nbr_j, int *pair_i, int *pair_j,
-                                int *pair_eij) {
+                                int *pair_eij, int *pair_img) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int e = nbr_off[i], h = half_off[i];
-  for_each_neighbor(c, shape, shapes, stride, G, cell_of, cell_start, cell_atoms, i, [&](int j) {
+  for_each_neighbor(c, shape, shapes, stride, G, cell_of, cell_start, cell_atoms, i, [&](int j, int img) {
     nbr_j[e] = j;
-    if (j > i) { pair_i[h] = i; pair_j[h] = j; pair_eij[h] = e; h++; }
+    if (j > i) { pair_i[h] = i; pair_j[h] = j; pair_eij[h] = e; pair_img[h] = img; h++; }
     e++;
   });
 }
-__global__ void pair_reverse_kernel(int npairs, const int *pair_i, const int *pair_j, const int *nbr_off,
+// reverse CSR entry of every pair.  Only OWNED atoms (index < nown) have CSR rows: for an owned-ghost pair there is no
+// reverse entry (the ghost's force belongs to another rank) and nbr_off[j] must not be read at all.
+__global__ void pair_reverse_kernel(int npairs, int nown, const int *pair_i, const int *pair_j, const int *nbr_off,
                                     const int *nbr_j, int *pair_eji) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= npairs) return;
   const int i = pair_i[p], j = pair_j[p];
   int found = -1;
-  for (int e = nbr_off[j]; e < nbr_off[j + 1]; e++)
-    if (nbr_j[e] == i) { found = e; break; }
+  if (j < nown)
+    for (int e = nbr_off[j]; e < nbr_off[j + 1]; e++)
+      if (nbr_j[e] == i) { found = e; break; }
   pair_eji[p] = found;
 }
 

@@ -30,6 +30,7 @@ struct PairArgs {
   const int *shape;
   int stride;
   const int *pair_i, *pair_j, *pair_eij, *pair_eji;
+  const int *pair_img;        // periodic image of the pair, 2 bits per dimension (n + 1), n = rint((c_i - c_j) / L) at the list build
   int npairs;
   double *slot;               // 6 x slot_stride : F(3), torque(3) per neighbor-list entry
   int slot_stride;
@@ -43,7 +44,21 @@ struct PairArgs {
   int max_terms, max_nq;      // shared-memory sizing
   int nlocal;                 // atoms >= nlocal are ghosts (counters[4] counts pairs with a ghost)
   const int *pair_list;       // optional indirection: process pairs pair_list[0..npairs) (deep-contact list)
+  const int *npairs_dev;      // optional: number of pairs lives on the device (deep-contact list of the split pipeline)
 };
+
+// minimum-image separation d = c_i - c_j - L n with the image n stored at the neighbor build: the same value, bit for
+// bit, as the oracle's d - L rint(d / L) (n = 0 leaves d untouched), without three FP64 divisions per pair and kernel
+__device__ __forceinline__ void pair_separation(const PairArgs &A, int p, int i, int j, double d[3]) {
+  const int st = A.stride, img = A.pair_img[p];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    double dk = A.c[k * st + i] - A.c[k * st + j];
+    const int n = ((img >> (2 * k)) & 3) - 1;
+    if (n != 0) dk = dk - A.boxlen[k] * (double)n;
+    d[k] = dk;
+  }
+}
 
 __host__ __device__ inline size_t pair_smem_bytes(int max_terms, int max_nq, int nwarps) {
   size_t b = 0;
@@ -83,12 +98,7 @@ __global__ void __launch_bounds__(NT) pair_kernel(PairArgs A) {
     const int st = A.stride;
     // minimum-image separation d = c_i - c_j (same ops as the oracle)
     double d[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      double dk = A.c[k * st + i] - A.c[k * st + j];
-      if (A.periodic[k]) dk = dk - A.boxlen[k] * rint(dk / A.boxlen[k]);
-      d[k] = dk;
-    }
+    pair_separation(A, p, i, j, d);
     const int shp_i = A.shape[i], shp_j = A.shape[j];
 
     for (int dir = 0; dir < 2; dir++) {

@@ -41,6 +41,9 @@ __global__ void __launch_bounds__(NW * 32) pair_warp_kernel(PairArgs A, int nsha
   unsigned short *s_ring = reinterpret_cast<unsigned short *>(s_pose + NW * 16);  // [NW][128]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // deep-contact list of the split pipeline: its length lives on the device (no host round trip)
+  const int npairs = A.npairs_dev ? *A.npairs_dev : A.npairs;
+  if (npairs == 0) return;
   if (SMEM_TABLES) {
     for (int s = 0; s < nshapes; s++) {
       const DevShape &sh = A.shapes[s];
@@ -58,16 +61,11 @@ __global__ void __launch_bounds__(NW * 32) pair_warp_kernel(PairArgs A, int nsha
     int p = 0;
     if (lane == 0) p = atomicAdd(A.work_counter, 1);
     p = __shfl_sync(0xffffffffu, p, 0);
-    if (p >= A.npairs) break;
+    if (p >= npairs) break;
     if (A.pair_list) p = A.pair_list[p];
     const int i = A.pair_i[p], j = A.pair_j[p];
     double d[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      double dk = A.c[k * st + i] - A.c[k * st + j];
-      if (A.periodic[k]) dk = dk - A.boxlen[k] * rint(dk / A.boxlen[k]);
-      d[k] = dk;
-    }
+    pair_separation(A, p, i, j, d);
     const int shp_i = A.shape[i], shp_j = A.shape[j];
     DirAcc acc;
     int ninside_pair = 0;
@@ -114,7 +112,7 @@ __global__ void __launch_bounds__(NW * 32) pair_warp_kernel(PairArgs A, int nsha
       const double *tabAp = SMEM_TABLES ? (s_Ap + sb.tab_off) : sb.Ap;
       const double2 *tabab = SMEM_TABLES ? (s_ab + sb.tab_off) : sb.ab;
       const int L = sb.lmax;
-      const float *__restrict__ cube = sb.cube_b2;
+      const float2 *__restrict__ cube = sb.cube_ul;
       const int cn = sb.cube_n;
       int queued = 0;  // ring holds entries [0, queued)
 
@@ -176,7 +174,7 @@ __global__ void __launch_bounds__(NW * 32) pair_warp_kernel(PairArgs A, int nsha
       const double D2 = e0 * e0 + e1 * e1 + e2 * e2, D = sqrt(D2);
       bool skip = D >= (sa.rmax + sb.rmax) * (1.0 + 1e-9);
       float cosA = -2.0f, xe = 1.0f, se = 0.0f, phie = 0.0f;
-      if (!skip && D > 1e-9) {
+      if (!skip && D > 1e-9 * (sa.rmax + sb.rmax)) {
         const double q = D2 - rmax2;
         double rc = sa.rmin;
         if (q > 0) rc = fmin(fmax(sqrt(q), sa.rmin), sa.rmax);
@@ -246,10 +244,14 @@ __global__ void __launch_bounds__(NW * 32) pair_warp_kernel(PairArgs A, int nsha
                     if (ax >= ay && ax >= az) { face = fx > 0 ? 0 : 1; ma = ax; uu = fy; vv = fz; }
                     else if (ay >= az) { face = fy > 0 ? 2 : 3; ma = ay; uu = fx; vv = fz; }
                     else { face = fz > 0 ? 4 : 5; ma = az; uu = fx; vv = fy; }
-                    const float im = 1.0f / ma, hn = 0.5f * (float)cn;
+                    const float im = 1.0f / fmaxf(ma, 1e-30f), hn = 0.5f * (float)cn;
                     const int iu = min(cn - 1, max(0, (int)((uu * im + 1.0f) * hn)));
                     const int iv = min(cn - 1, max(0, (int)((vv * im + 1.0f) * hn)));
-                    surv = rho2 < (double)__ldg(&cube[(face * cn + iu) * cn + iv]);
+                    // proven bounds of r^2 over the cell: below the lower bound the node is inside, at or above
+                    // the upper bound it is outside, in between the series decides
+                    const float2 ul = __ldg(&cube[(face * cn + iu) * cn + iv]);
+                    if (rho2 <= (double)ul.y) accumulate(k, p0, p1, p2);
+                    else surv = rho2 < (double)ul.x;
                   } else surv = true;
                 }
               }

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <thread>
 
 namespace shgpu {
 
@@ -164,96 +165,135 @@ double radius_for_bounds(const ShapeTables &s, double s0, double s1, double s2) 
   return r;
 }
 
-// cube-map direction cells: face f in 0..5 = +x,-x,+y,-y,+z,-z; (u,v) = the two other components (in x,y,z
-// order) divided by |major|; cell (iu,iv) = floor((u+1)/2*n).  Samples overlap one sub-step into the
-// neighbouring cells / faces and the bound is padded by the largest adjacent-sample difference, so that an
-// FP32 cell index (pair_warp_kernel.cuh) that lands in a neighbouring cell near a border is still covered.
-void build_cube_bounds(ShapeTables &s, int n, int sub) {
-  s.cube_n = n;
-  s.cube_bound2.assign((size_t)6 * n * n, 0.0f);
-  const int ns = n * sub + 3;                  // samples per face edge: indices -1 .. n*sub+1
-  std::vector<double> r((size_t)ns * ns);
-  for (int f = 0; f < 6; f++) {
-    const int major = f / 2;
-    const double sgn = (f % 2) ? -1.0 : 1.0;
-    for (int a = 0; a < ns; a++)
-      for (int b = 0; b < ns; b++) {
-        const double u = -1.0 + 2.0 * (a - 1) / (double)(n * sub), v = -1.0 + 2.0 * (b - 1) / (double)(n * sub);
-        double d[3];
-        d[major] = sgn;
-        d[major == 0 ? 1 : 0] = u;
-        d[major == 2 ? 1 : 2] = v;
-        r[(size_t)a * ns + b] = radius_for_bounds(s, d[0], d[1], d[2]);
-      }
-    for (int iu = 0; iu < n; iu++)
-      for (int iv = 0; iv < n; iv++) {
-        double mx = 0, dmax = 0;
-        for (int a = iu * sub; a <= (iu + 1) * sub + 2; a++)
-          for (int b = iv * sub; b <= (iv + 1) * sub + 2; b++) {
-            const double v0 = r[(size_t)a * ns + b];
-            mx = std::max(mx, v0);
-            if (a + 1 < ns) dmax = std::max(dmax, std::fabs(r[(size_t)(a + 1) * ns + b] - v0));
-            if (b + 1 < ns) dmax = std::max(dmax, std::fabs(r[(size_t)a * ns + b + 1] - v0));
-          }
-        const double bound = (mx + dmax) * (1.0 + 1e-6);
-        float b2 = (float)(bound * bound);
-        b2 = std::nextafter(b2, 3.0e38f);      // round up: the FP32 value must not be below the FP64 bound^2
-        s.cube_bound2[((size_t)f * n + iu) * n + iv] = b2;
-      }
+// ---- rigorous direction-cell tables ------------------------------------------------------------
+// Derivative bounds.  Write r = sum_l f_l with f_l the degree-l part.  In the orthonormal real basis the
+// coefficient vector of f_l is c_l = (a_l0, a_lm/sqrt2, b_lm/sqrt2), so by Cauchy-Schwarz and the addition theorem
+// (sum_m Y_lm^2 = (2l+1)/4pi)   |f_l| <= B_l := sqrt((2l+1)/4pi) |c_l|_2   everywhere.  Restricted to a great circle
+// parametrised by arc length t, f_l is a trigonometric polynomial of degree <= l, so Bernstein's inequality gives
+// |f_l'| <= l B_l and |f_l''| <= l^2 B_l.  Hence  |dr/dt| <= H1 = sum l B_l,  |d2r/dt2| <= H2 = sum l^2 B_l.
+void derivative_bounds(ShapeTables &s) {
+  double h1 = 0, h2 = 0;
+  for (int l = 1; l <= s.lmax; l++) {
+    double n2 = s.a_raw[lm(l, 0)] * s.a_raw[lm(l, 0)];
+    for (int m = 1; m <= l; m++) n2 += 0.5 * (s.a_raw[lm(l, m)] * s.a_raw[lm(l, m)] + s.b_raw[lm(l, m)] * s.b_raw[lm(l, m)]);
+    const double B = std::sqrt((2.0 * l + 1.0) / (4.0 * kPi)) * std::sqrt(n2);
+    h1 += l * B;
+    h2 += (double)l * l * B;
   }
+  s.h1_bound = h1 * (1.0 + 1e-12);
+  s.h2_bound = h2 * (1.0 + 1e-12);
 }
 
-// Table for the candidate cache (pair_split_kernels.cuh).  A node cached at build time with direction d0 (as
-// seen from this shape's centre) and radius rho0 may move by at most delta before the cache is rebuilt, so its
-// direction drifts by at most gamma = asin(delta / (rmin + 2 delta)) (nodes closer than rmin + 2 delta are cached
-// unconditionally).  wide2(cell) = (sqrt(max cube_bound2 over all cells within gamma of the cell) + delta)^2.
-void build_cache_table(ShapeTables &s) {
-  const int n = s.cube_n;
-  s.cache_delta = 0.02 * s.rmax;
-  const double ratio = s.cache_delta / (s.rmin + 2.0 * s.cache_delta);
-  const double gamma = 1.1 * std::asin(std::min(1.0, ratio)) + 1e-3;
-  std::vector<double> dir((size_t)6 * n * n * 3), hd((size_t)6 * n * n);
-  auto cell_dir = [&](int f, double u, double v, double *d) {
-    const int major = f / 2;
-    d[major] = (f % 2) ? -1.0 : 1.0;
-    d[major == 0 ? 1 : 0] = u;
-    d[major == 2 ? 1 : 2] = v;
-    const double nn = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-    for (int k = 0; k < 3; k++) d[k] /= nn;
-  };
-  const double du = 2.0 / n, ov = du / 6.0;   // cells cover their own extent plus the one-sub-step overlap
+// Cube map: face f in 0..5 = +x,-x,+y,-y,+z,-z; (u,v) = the two other components (in x,y,z order) divided by |major|
+// (gnomonic coordinates); cell (iu,iv) = floor((u+1)/2*n).  Straight lines in (u,v) are great-circle arcs and the
+// map (u,v) -> direction is a contraction, so on a gnomonic grid of spacing D every direction x inside a grid square
+// satisfies  min(corners) - H2 D^2/4 <= r(x) <= max(corners) + H2 D^2/4  (interpolation error of a function with
+// |f''| <= H2 on a segment of length <= D, applied along v = const and then along the two u = const edges).
+// The FP32 cell index of the kernels can be off by one cell for directions within ~1e-6 of a border; the term
+// H1 * 1e-5 covers a border strip of width 1e-5 in (u,v).
+// The sample grid of every face extends K steps beyond the face (directions (1,u,v) with |u| > 1 are ordinary
+// directions) so that the candidate-cache tables can look across face edges.
+struct FaceSamples {
+  int ns = 0, K = 0, NS = 0;     // ns = NS + 2K + 1 samples per edge, u_a = -1 + (a - K) * step
+  double step = 0;
+  std::vector<double> r[6];
+};
+
+static void face_direction(int f, double u, double v, double d[3]) {
+  const int major = f / 2;
+  d[major] = (f % 2) ? -1.0 : 1.0;
+  d[major == 0 ? 1 : 0] = u;
+  d[major == 2 ? 1 : 2] = v;
+}
+
+void sample_faces(const ShapeTables &s, int NS, int K, FaceSamples &F) {
+  F.NS = NS; F.K = K; F.ns = NS + 2 * K + 1; F.step = 2.0 / NS;
+  const int ns = F.ns;
+  for (int f = 0; f < 6; f++) F.r[f].assign((size_t)ns * ns, 0.0);
+  const int nthreads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nthreads; t++)
+    pool.emplace_back([&, t]() {
+      for (int job = t; job < 6 * ns; job += nthreads) {
+        const int f = job / ns, a = job % ns;
+        const double u = -1.0 + (a - K) * F.step;
+        for (int b = 0; b < ns; b++) {
+          double d[3];
+          face_direction(f, u, -1.0 + (b - K) * F.step, d);
+          F.r[f][(size_t)a * ns + b] = radius_for_bounds(s, d[0], d[1], d[2]);
+        }
+      }
+    });
+  for (auto &th : pool) th.join();
+}
+
+static inline float sq_up(double v) { float q = (float)(v * v); return std::nextafter(q, 3.0e38f); }
+static inline float sq_down(double v) { float q = (float)(v * v); return std::nextafter(q, 0.0f); }
+
+const double kCacheFrac[SH_CACHE_LEVELS] = {0.005, 0.01, 0.02};   // cache_delta[level] / rmax
+
+std::string build_cube_tables(ShapeTables &s, int n) {
+  derivative_bounds(s);
+  const int sub = std::max(n <= 144 ? 2 : 1, (144 + n / 2) / n), NS = n * sub;   // sample spacing <= 2/144 whatever the cell size
+  const double step = 2.0 / NS;
+  for (int lv = 0; lv < SH_CACHE_LEVELS; lv++) s.cache_delta[lv] = kCacheFrac[lv] * s.rmax;
+  // direction drift of a node that moves by <= delta at distance >= rmin + 2 delta from the centre
+  double gamma[SH_CACHE_LEVELS];
+  for (int lv = 0; lv < SH_CACHE_LEVELS; lv++)
+    gamma[lv] = std::asin(std::min(1.0, s.cache_delta[lv] / (s.rmin + 2.0 * s.cache_delta[lv]))) * (1.0 + 1e-9) + 1e-9;
+  const double eps_uv = 1e-5;
+  const int K = (int)std::ceil(3.6 * gamma[SH_CACHE_LEVELS - 1] / step) + 3;
+  FaceSamples F;
+  sample_faces(s, NS, K, F);
+  const int ns = F.ns;
+  s.cube_n = n;
+  s.sample_step = step;
+  s.sample_pad = 0.25 * s.h2_bound * step * step + s.h1_bound * eps_uv;
+  const size_t nc = (size_t)6 * n * n;
+  s.cube_ub2.assign(nc, 0.0f); s.cube_lb2.assign(nc, 0.0f);
+  for (int lv = 0; lv < SH_CACHE_LEVELS; lv++) s.cube_wide2[lv].assign(nc, 0.0f);
+  double rsup = 0, rinf = 1e300;
+  std::vector<double> ubv(nc), lbv(nc);
   for (int f = 0; f < 6; f++)
     for (int iu = 0; iu < n; iu++)
       for (int iv = 0; iv < n; iv++) {
         const size_t c = ((size_t)f * n + iu) * n + iv;
-        const double u0 = -1.0 + iu * du, v0 = -1.0 + iv * du;
-        cell_dir(f, u0 + 0.5 * du, v0 + 0.5 * du, &dir[3 * c]);
-        double worst = 0;
-        for (int a = 0; a < 2; a++)
-          for (int b = 0; b < 2; b++) {
-            double cd[3];
-            cell_dir(f, u0 - ov + a * (du + 2 * ov), v0 - ov + b * (du + 2 * ov), cd);
-            const double dot = cd[0] * dir[3 * c] + cd[1] * dir[3 * c + 1] + cd[2] * dir[3 * c + 2];
-            worst = std::max(worst, std::acos(std::min(1.0, std::max(-1.0, dot))));
-          }
-        hd[c] = worst;   // angular half-diagonal of the (overlapped) cell
+        const int a0 = K + iu * sub, a1 = K + (iu + 1) * sub, b0 = K + iv * sub, b1 = K + (iv + 1) * sub;
+        double mx = 0, mn = 1e300;
+        for (int a = a0; a <= a1; a++)
+          for (int b = b0; b <= b1; b++) { const double v = F.r[f][(size_t)a * ns + b]; mx = std::max(mx, v); mn = std::min(mn, v); }
+        ubv[c] = (mx + s.sample_pad) * (1.0 + 1e-12);
+        lbv[c] = (mn - s.sample_pad) * (1.0 - 1e-12);
+        rsup = std::max(rsup, ubv[c]); rinf = std::min(rinf, lbv[c]);
+        // candidate-cache tables: every direction within gamma of the (border-extended) cell.  An arc of length g
+        // stays within (u,v)-distance rho of its start if g * (1 + R2(rho)) <= rho, R2 = max u^2+v^2 over the box + rho.
+        const double ulo = -1.0 + iu * (2.0 / n), uhi = ulo + 2.0 / n, vlo = -1.0 + iv * (2.0 / n), vhi = vlo + 2.0 / n;
+        for (int lv = 0; lv < SH_CACHE_LEVELS; lv++) {
+          auto stretch = [&](double rho) {
+            const double um = std::max(std::fabs(ulo), std::fabs(uhi)) + rho + eps_uv, vm = std::max(std::fabs(vlo), std::fabs(vhi)) + rho + eps_uv;
+            return 1.0 + um * um + vm * vm;
+          };
+          double rho = gamma[lv] * stretch(0.0);
+          for (int it = 0; it < 60 && gamma[lv] * stretch(rho) > rho; it++) rho = gamma[lv] * stretch(rho) * 1.02;
+          if (gamma[lv] * stretch(rho) > rho) return "candidate-cache table: drift radius did not converge";
+          const int e = (int)std::ceil((rho + eps_uv) / step);
+          if (a0 - e < 0 || b0 - e < 0 || a1 + e >= ns || b1 + e >= ns) return "candidate-cache table: sample grid too small";
+          double wm = 0;
+          for (int a = a0 - e; a <= a1 + e; a++)
+            for (int b = b0 - e; b <= b1 + e; b++) wm = std::max(wm, F.r[f][(size_t)a * ns + b]);
+          const double w = (wm + s.sample_pad) * (1.0 + 1e-12) + s.cache_delta[lv];
+          s.cube_wide2[lv][c] = sq_up(w);
+        }
       }
-  const size_t nc = (size_t)6 * n * n;
-  s.cube_wide2.assign(nc, 0.0f);
-  double hdmax = 0;
-  for (size_t c = 0; c < nc; c++) hdmax = std::max(hdmax, hd[c]);
-  const double reach = gamma + 2.0 * hdmax + 1e-6;
-  const double cos_reach = reach >= 3.14159 ? -2.0 : std::cos(reach);
+  s.r_sup = rsup; s.r_inf = rinf;
+  // rmax / rmin (shared bit for bit with the oracle: 4x oversampled node grid, 0.5 % pad) must be PROVEN bounds
+  if (!(rsup <= s.rmax)) return "cannot prove the bounding radius: sup r <= " + std::to_string(rsup) + " > rmax = " + std::to_string(s.rmax) + " (shape too rough for the 0.5 % pad)";
+  if (!(rinf >= s.rmin)) return "cannot prove the inscribed radius: inf r >= " + std::to_string(rinf) + " < rmin = " + std::to_string(s.rmin) + " (shape too rough for the 0.5 % pad)";
   for (size_t c = 0; c < nc; c++) {
-    float mx = 0.0f;
-    for (size_t e = 0; e < nc; e++) {
-      const double dot = dir[3 * c] * dir[3 * e] + dir[3 * c + 1] * dir[3 * e + 1] + dir[3 * c + 2] * dir[3 * e + 2];
-      if (dot >= cos_reach) mx = std::max(mx, s.cube_bound2[e]);
-    }
-    const double w = std::sqrt((double)mx) + s.cache_delta;
-    float w2 = (float)(w * w * (1.0 + 1e-6));
-    s.cube_wide2[c] = std::nextafter(w2, 3.0e38f);
+    s.cube_ub2[c] = sq_up(std::min(ubv[c], s.rmax));
+    s.cube_lb2[c] = sq_down(std::max(lbv[c], s.rmin));
   }
+  return "";
 }
 
 // cyclic Jacobi for a symmetric 3x3 (principal inertia axes)
@@ -312,7 +352,7 @@ void quat_from_rotation(double R[3][3], double q[4]) {
 }  // namespace
 
 std::string build_shape_tables(int lmax, const double *a_lm, const double *b_lm, double density, int n_theta,
-                               int n_phi, ShapeTables &s) {
+                               int n_phi, ShapeTables &s, int cube_n) {
   if (lmax < 0 || lmax > 128) return "lmax out of range";
   if (!(density > 0)) return "density must be > 0";
   if (!a_lm) return "a_lm is NULL";
@@ -391,9 +431,7 @@ std::string build_shape_tables(int lmax, const double *a_lm, const double *b_lm,
   quat_from_rotation(V, qp);
   for (int d = 0; d < 4; d++) s.quat_principal[d] = qp[d];
   rotation_from_quat(qp, s.Rp);
-  build_cube_bounds(s, 24, 6);
-  build_cache_table(s);
-  return "";
+  return build_cube_tables(s, cube_n > 0 ? cube_n : 144);
 }
 
 }  // namespace shgpu

@@ -21,14 +21,20 @@ struct ShapeTables {
   std::vector<double> ah, bh;            // coefficients with alpha_lm * c_m folded in
   // node table, SoA: px,py,pz, nx,ny,nz (oriented area elements n dS)
   std::vector<double> node_p[3], node_n[3];
-  // conservative squared upper bound of r over the cells of a cube map of directions (6 x cube_n x cube_n):
-  // a node with rho^2 >= bound2(cell(direction)) is certainly outside, no SH evaluation needed
+  // Direction-cell tables over a cube map of directions (6 faces x cube_n x cube_n gnomonic cells), all RIGOROUS
+  // (DESIGN §4.0): r is sampled on a gnomonic grid of spacing sample_step per face; between samples it is bounded with
+  // the second-derivative bound h2_bound (Bernstein inequality per harmonic degree), so that
+  //   cube_ub2[cell] >= r(d)^2 >= cube_lb2[cell]   for every direction d whose FP32 cell index is `cell`.
+  // A node with rho^2 >= ub2 is outside and one with rho^2 <= lb2 is inside, without evaluating the series.
   int cube_n = 0;
-  std::vector<float> cube_bound2;
-  // candidate-cache table: (sqrt(max of cube_bound2 over all cells within the angle a node direction can drift
-  // before the cache is rebuilt) + cache_delta)^2; cache_delta = node displacement margin of the cache
-  std::vector<float> cube_wide2;
-  double cache_delta = 0;
+  std::vector<float> cube_ub2, cube_lb2;
+  // candidate-cache tables, one per margin level: (max of r over every direction a node direction can drift to before
+  // the cache is rebuilt + cache_delta[level])^2; cache_delta = node displacement margin of that level
+  std::vector<float> cube_wide2[3];
+  double cache_delta[3] = {0, 0, 0};
+  double h1_bound = 0, h2_bound = 0;     // sup |dr/dt|, sup |d2r/dt2| along great circles (t = arc length), rigorous
+  double sample_step = 0, sample_pad = 0;   // gnomonic sample spacing and the interpolation pad h2 step^2/4 (+ border term)
+  double r_sup = 0, r_inf = 0;           // proven bounds of r over the sphere (max ub, min lb); rmax/rmin are checked against them
   std::vector<double> row_x;             // cos(theta) of the Gauss-Legendre rows (node k = row*n_phi+col)
   double density = 1, volume = 0, mass = 0;
   std::array<double, 3> com{}, inertia{};
@@ -38,8 +44,9 @@ struct ShapeTables {
 };
 
 // Returns "" on success, else an error message.
+constexpr int SH_CACHE_LEVELS = 3;
 std::string build_shape_tables(int lmax, const double *a_lm, const double *b_lm, double density,
-                               int n_theta, int n_phi, ShapeTables &out);
+                               int n_theta, int n_phi, ShapeTables &out, int cube_n = 0);
 
 void gauss_legendre_nodes(int n, std::vector<double> &x, std::vector<double> &w);
 void legendre_normalised(int lmax, double x, std::vector<double> &P);

@@ -42,7 +42,9 @@ struct DevBuf {
 struct ShapeDev {
   DevBuf<double> Ap, node;   // node: 6 x nq
   DevBuf<double2> ab;
-  DevBuf<float> row_x, cube, pf, cubew;
+  DevBuf<float> row_x, cubew[SH_CACHE_LEVELS];
+  DevBuf<float2> cube;       // {ub2, lb2} per direction cell
+  DevBuf<float4> pf4;        // FP32 node points
 };
 
 }  // namespace
@@ -77,24 +79,35 @@ struct sh_ctx {
   std::vector<int64_t> tag;
   // neighbor
   DevBuf<int> cell_of, cell_count, cell_start, cell_fill, cell_atoms, tile_sum, cnt_full, cnt_half, nbr_off, half_off,
-      nbr_j, pair_i, pair_j, pair_eij, pair_eji, scalars;  // scalars: [0]=total [1]=rebuild flag [2]=work counter
+      nbr_j, pair_i, pair_j, pair_eij, pair_eji, pair_img, scalars;  // scalars: [0]=total [1]=rebuild flag [2]=work counter
   DevBuf<double> bbox, slot, pres, stage;
   // split pair pipeline (pair_split_kernels.cuh)
   DevBuf<SurvRec> pool;
   DevBuf<unsigned char> pool_flag;
-  DevBuf<long long> pool_base, pool_cap, pd_off;
-  DevBuf<unsigned long long> pool_count;
-  DevBuf<int> pd_cnt, big_list, split_flags;   // split_flags: [0]=nbig [1]=overflow
+  DevBuf<long long> pool_base, pool_cap;
+  DevBuf<PdEntry> pd;
+  DevBuf<PairHot> cache_hot;
+  DevBuf<SplitScalars> split_sc;
+  DevBuf<EvalPlanDev> eval_plan;
+  DevBuf<int> big_list, slow_list, split_flags;   // split_flags: [2]=cache overflow
   std::vector<long long> h_pool_cap;
-  unsigned long long *h_pool_count = nullptr;  // pinned: [nshape] counts, then nbig, overflow
-  cudaEvent_t ev_b0 = nullptr, ev_b1 = nullptr;
-  double sec_eval = 0, sec_cull = 0, sec_reduce = 0, sec_deep = 0; int64_t eval_launches = 0;
+  unsigned long long *h_pool_count = nullptr;  // pinned scratch for cache builds
+  SplitScalars *h_split_sc = nullptr;          // pinned: advisory read-back of the previous pair phase
+  int *h_cache_invalid = nullptr;              // pinned
+  cudaEvent_t ev_sc = nullptr;                 // recorded after the read-back copies
+  bool sc_pending = false;
+  int sc_nshape = 0;
+  double sec_eval = 0, sec_cull = 0, sec_reduce = 0, sec_deep = 0, sec_cache = 0; int64_t eval_launches = 0;
   std::vector<int> ev2_kind;
-  int64_t big_pairs = 0, split_redo = 0, cache_builds = 0;
+  int64_t big_pairs = 0, slow_pairs = 0, pool_grows = 0, cache_builds = 0;
+  int cache_level = 0, cache_level_pin = -1;   // margin level of the candidate cache (adaptive unless pinned)
+  int64_t cache_age = 0;                       // pair phases since the last cache build
+  bool cache_exhausted = false;                // the last invalidation came from the displacement margin
+  int cube_n = 0;                              // direction cells per cube-face edge (0 = default)
+  int eval_pts = 0, eval_occ = 0, eval_mode = 0;   // pair_eval_kernel: points per lane, min CTAs/SM, 1 = one block per CTA
+  long long last_records = 0;                  // records of the previous pair phase (advisory)
   // candidate cache
   DevBuf<unsigned short> cache_pool;
-  DevBuf<long long> cache_off;
-  DevBuf<int> cache_cnt;
   DevBuf<unsigned long long> cache_count;
   long long cache_cap = 0;
   bool cache_valid = false;
@@ -114,7 +127,7 @@ struct sh_ctx {
   cudaEvent_t run_e0 = nullptr, run_e1 = nullptr;
   int64_t pair_launches = 0;
   // tuning
-  int tune_threads = 0, tune_ctas_per_sm = 0, tune_variant = 0;
+  int tune_threads = 0, tune_ctas_per_sm = 0, tune_variant = 0, tune_cull_wpb = 0, tune_cull_lpp = 0;
 };
 
 namespace {
@@ -154,14 +167,18 @@ int upload_shapes(sh_ctx *h) {
       {
         std::vector<float> rx(t.row_x.begin(), t.row_x.end());
         CU(cudaMemcpy(d.row_x.p, rx.data(), rx.size() * sizeof(float), cudaMemcpyHostToDevice));
-        std::vector<float> pf((size_t)3 * t.nq);
-        for (int e = 0; e < 3; e++) for (int k = 0; k < t.nq; k++) pf[(size_t)e * t.nq + k] = (float)t.node_p[e][k];
-        d.pf.ensure(pf.size());
-        CU(cudaMemcpy(d.pf.p, pf.data(), pf.size() * sizeof(float), cudaMemcpyHostToDevice));
-        d.cubew.ensure(t.cube_wide2.size());
-        CU(cudaMemcpy(d.cubew.p, t.cube_wide2.data(), t.cube_wide2.size() * sizeof(float), cudaMemcpyHostToDevice));
-        d.cube.ensure(t.cube_bound2.size());
-        CU(cudaMemcpy(d.cube.p, t.cube_bound2.data(), t.cube_bound2.size() * sizeof(float), cudaMemcpyHostToDevice));
+        std::vector<float4> pf((size_t)t.nq);
+        for (int k = 0; k < t.nq; k++) pf[k] = make_float4((float)t.node_p[0][k], (float)t.node_p[1][k], (float)t.node_p[2][k], 0.0f);
+        d.pf4.ensure(pf.size());
+        CU(cudaMemcpy(d.pf4.p, pf.data(), pf.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        for (int lv = 0; lv < SH_CACHE_LEVELS; lv++) {
+          d.cubew[lv].ensure(t.cube_wide2[lv].size());
+          CU(cudaMemcpy(d.cubew[lv].p, t.cube_wide2[lv].data(), t.cube_wide2[lv].size() * sizeof(float), cudaMemcpyHostToDevice));
+        }
+        std::vector<float2> ul(t.cube_ub2.size());
+        for (size_t c = 0; c < ul.size(); c++) ul[c] = make_float2(t.cube_ub2[c], t.cube_lb2[c]);
+        d.cube.ensure(ul.size());
+        CU(cudaMemcpy(d.cube.p, ul.data(), ul.size() * sizeof(float2), cudaMemcpyHostToDevice));
       }
       std::vector<double2> ab(t.nterms);
       for (int k = 0; k < t.nterms; k++) ab[k] = make_double2(t.ah[k], t.bh[k]);
@@ -180,7 +197,8 @@ int upload_shapes(sh_ctx *h) {
       v.Ap = d.Ap.p; v.ab = d.ab.p;
       v.px = d.node.p; v.py = d.node.p + t.nq; v.pz = d.node.p + 2 * (size_t)t.nq;
       v.nx = d.node.p + 3 * (size_t)t.nq; v.ny = d.node.p + 4 * (size_t)t.nq; v.nz = d.node.p + 5 * (size_t)t.nq;
-      v.n_theta = t.n_theta; v.n_phi = t.n_phi; v.nterms4 = (t.nterms + 3) / 4 * 4; v.row_x = d.row_x.p; v.cube_b2 = d.cube.p; v.cube_n = t.cube_n; v.pad2_ = 0; v.pf = d.pf.p; v.cube_w2 = d.cubew.p; v.cache_delta = t.cache_delta;
+      v.n_theta = t.n_theta; v.n_phi = t.n_phi; v.nterms4 = (t.nterms + 3) / 4 * 4; v.row_x = d.row_x.p; v.cube_ul = d.cube.p; v.cube_n = t.cube_n; v.pad2_ = 0; v.pf4 = d.pf4.p;
+      for (int lv = 0; lv < SH_CACHE_LEVELS; lv++) { v.cube_w2[lv] = d.cubew[lv].p; v.cache_delta[lv] = t.cache_delta[lv]; }
     }
     int off = 0;
     for (int s = 0; s < ns; s++) { h->shape_host_view[s].tab_off = off; off += h->shape_host_view[s].nterms4 + 4; }
@@ -292,14 +310,14 @@ int build_neighbors(sh_ctx *h) {
   if (exclusive_scan(h, h->cnt_half.p, h->half_off.p, nown, &npairs)) return -1;
   try {
     h->nbr_j.ensure(nentries + 1); h->pair_i.ensure(npairs + 1); h->pair_j.ensure(npairs + 1);
-    h->pair_eij.ensure(npairs + 1); h->pair_eji.ensure(npairs + 1);
+    h->pair_eij.ensure(npairs + 1); h->pair_eji.ensure(npairs + 1); h->pair_img.ensure(npairs + 1);
     if ((size_t)nentries + 1 > (size_t)h->slot_stride) { h->slot_stride = (int)((nentries + 1) * 1.25) + 64; h->slot.release(); h->slot.ensure((size_t)6 * h->slot_stride); }
     if ((size_t)npairs + 1 > (size_t)h->pres_stride) { h->pres_stride = (int)((npairs + 1) * 1.25) + 64; h->pres.release(); h->pres.ensure((size_t)14 * h->pres_stride); }
   } catch (std::string &e) { return fail(h, e); }
   nbr_fill_kernel<<<nbo, 256, 0, h->stream>>>(h->c.p, h->shape.p, h->d_shapes.p, nown, st, G, h->cell_of.p, h->cell_start.p,
                                              h->cell_atoms.p, h->nbr_off.p, h->half_off.p, h->nbr_j.p, h->pair_i.p,
-                                             h->pair_j.p, h->pair_eij.p);
-  pair_reverse_kernel<<<std::max(1, cdiv(npairs, 256)), 256, 0, h->stream>>>(npairs, h->pair_i.p, h->pair_j.p, h->nbr_off.p,
+                                             h->pair_j.p, h->pair_eij.p, h->pair_img.p);
+  pair_reverse_kernel<<<std::max(1, cdiv(npairs, 256)), 256, 0, h->stream>>>(npairs, nown, h->pair_i.p, h->pair_j.p, h->nbr_off.p,
                                                                              h->nbr_j.p, h->pair_eji.p);
   copy_origin_kernel<<<nb, 256, 0, h->stream>>>(h->c.p, h->c0.p, n, st);
   h->kernel_launches += 3;
@@ -322,8 +340,8 @@ int drain_events(sh_ctx *h) {
   for (size_t k = 0; k + 1 < h->ev2_used; k += 2) {
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev2[k], h->ev2[k + 1]);
-    double *dst[4] = {&h->sec_cull, &h->sec_eval, &h->sec_reduce, &h->sec_deep};
-    *dst[h->ev2_kind[k / 2] & 3] += ms * 1e-3;
+    double *dst[8] = {&h->sec_cull, &h->sec_eval, &h->sec_reduce, &h->sec_deep, &h->sec_cache, &h->sec_other, &h->sec_other, &h->sec_other};
+    *dst[h->ev2_kind[k / 2] & 7] += ms * 1e-3;
   }
   h->ev2_used = 0;
   for (size_t k = 0; k + 1 < h->ev_used; k += 2) {
@@ -348,67 +366,127 @@ int launch_pair(sh_ctx *h, const PairArgs &A, int ctas_per_sm, size_t smem) {
 }
 
 template <int NW, bool SMEM_TABLES>
-int launch_pair_warp(sh_ctx *h, const PairArgs &A, int ctas_per_sm) {
+int launch_pair_warp(sh_ctx *h, const PairArgs &A, int ctas_per_sm, int max_grid = 1 << 30) {
   const size_t smem = pair_warp_smem_bytes(h->total_terms, NW, SMEM_TABLES);
   CU(cudaFuncSetAttribute(pair_warp_kernel<NW, SMEM_TABLES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
   int occ = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pair_warp_kernel<NW, SMEM_TABLES>, NW * 32, smem));
   if (occ < 1) return fail(h, "pair warp kernel does not fit on an SM");
   if (ctas_per_sm > 0) occ = std::min(occ, ctas_per_sm);
-  const int grid = std::max(1, std::min((A.npairs + NW - 1) / NW, occ * h->sm_count));
+  const int grid = std::max(1, std::min(std::min((A.npairs + NW - 1) / NW, occ * h->sm_count), max_grid));
   pair_warp_kernel<NW, SMEM_TABLES><<<grid, NW * 32, smem, h->stream>>>(A, (int)h->shapes.size(), h->total_terms, (h->tune_variant & 2) ? 0 : 1);
   return 0;
 }
 
-int launch_fused(sh_ctx *h, const PairArgs &P) {
+int launch_fused(sh_ctx *h, const PairArgs &P, int max_grid = 1 << 30) {
   const bool fits = pair_warp_smem_bytes(h->total_terms, 16, true) <= 200 * 1024;
   const int tw = h->tune_threads ? h->tune_threads : 512;
+  const int cps = h->tune_ctas_per_sm;
   if (fits) {
-    if (tw == 256) return launch_pair_warp<8, true>(h, P, h->tune_ctas_per_sm);
-    if (tw == 128) return launch_pair_warp<4, true>(h, P, h->tune_ctas_per_sm);
-    if (tw == 384) return launch_pair_warp<12, true>(h, P, h->tune_ctas_per_sm);
-    return launch_pair_warp<16, true>(h, P, h->tune_ctas_per_sm);
+    if (tw == 256) return launch_pair_warp<8, true>(h, P, cps, max_grid);
+    if (tw == 128) return launch_pair_warp<4, true>(h, P, cps, max_grid);
+    if (tw == 384) return launch_pair_warp<12, true>(h, P, cps, max_grid);
+    return launch_pair_warp<16, true>(h, P, cps, max_grid);
   }
-  if (tw == 256) return launch_pair_warp<8, false>(h, P, h->tune_ctas_per_sm);
-  return launch_pair_warp<16, false>(h, P, h->tune_ctas_per_sm);
+  if (tw == 256) return launch_pair_warp<8, false>(h, P, cps, max_grid);
+  return launch_pair_warp<16, false>(h, P, cps, max_grid);
 }
 
-// cull -> (host reads the pool counters) -> evaluate -> reduce (+ fused kernel on the deep-contact list)
+template <int WPB, int PTS, int MINB>
+int launch_eval(sh_ctx *h, const SplitArgs &S, int maxT) {
+  const size_t smem = (size_t)maxT * 24 + 32;
+  auto kern = pair_eval_kernel<WPB, PTS, MINB>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+  int occ = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WPB * 32, smem));
+  if (occ < 1) return fail(h, "pair_eval_kernel does not fit on an SM");
+  const int rpb = WPB * 32 * PTS;
+  eval_plan_kernel<<<1, 32, 0, h->stream>>>(S, (int)h->shapes.size(), rpb, h->eval_plan.p);
+  const int chunked = h->eval_mode == 2;
+  int grid = occ * h->sm_count;
+  if (!chunked) {   // one block per CTA: grid from the previous phase's record count (+ slack), grid-stride covers the rest
+    long long est = h->last_records > 0 ? h->last_records + h->last_records / 16 : 0;
+    if (est == 0) for (long long c : h->h_pool_cap) est += c;
+    grid = (int)std::max<long long>(grid, std::min<long long>(est / rpb + (long long)h->shapes.size() + 1, 1 << 22));
+  }
+  kern<<<grid, WPB * 32, smem, h->stream>>>(h->d_shapes.p, S, h->eval_plan.p, h->counters.p, chunked);
+  h->kernel_launches += 2;
+  return 0;
+}
+
+// advisory read-back of the previous pair phase (pool fill, deep / slow pairs, cache validity): never needed for the
+// correctness of that phase (a full pool sends pairs to the fused kernel), only to size the next one
+int absorb_split_feedback(sh_ctx *h) {
+  if (!h->sc_pending) return 0;
+  CU(cudaEventSynchronize(h->ev_sc));
+  h->sc_pending = false;
+  const SplitScalars &sc = *h->h_split_sc;
+  h->big_pairs += sc.nbig; h->slow_pairs += sc.nslow;
+  const int ns = std::min<int>(h->sc_nshape, (int)h->h_pool_cap.size());
+  for (int s = 0; s < ns; s++)
+    if ((long long)sc.pool_count[s] > h->h_pool_cap[s] * 9 / 10) {
+      h->h_pool_cap[s] = (long long)(sc.pool_count[s] * 3 / 2) + 4096;
+      h->pool_grows++;
+    }
+  h->last_records = 0;
+  for (int s = 0; s < ns; s++) h->last_records += (long long)std::min<unsigned long long>(sc.pool_count[s], (unsigned long long)h->h_pool_cap[s]);
+  if (*h->h_cache_invalid != 0 && h->cache_valid) { h->cache_valid = false; h->cache_exhausted = true; }
+  return 0;
+}
+
+// cached cull (+ window cull on the slow list) -> evaluate -> reduce -> fused kernel on the deep-contact list.
+// Nothing in here waits for the device except a candidate-cache (re)build.
 int run_split_pipeline(sh_ctx *h, PairArgs &P) {
   const int ns = (int)h->shapes.size(), np = P.npairs;
   constexpr int WPB = 8;
+  int rc;
+  if ((rc = absorb_split_feedback(h))) return rc;
   try {
-    h->pd_off.ensure((size_t)2 * np + 2); h->pd_cnt.ensure((size_t)2 * np + 2); h->big_list.ensure(np + 1);
-    h->pool_base.ensure(SH_MAX_SHAPES); h->pool_cap.ensure(SH_MAX_SHAPES); h->pool_count.ensure(SH_MAX_SHAPES); h->split_flags.ensure(4);
+    h->pd.ensure((size_t)2 * np + 2); h->big_list.ensure(np + 1); h->slow_list.ensure(np + 1);
+    h->pool_base.ensure(SH_MAX_SHAPES); h->pool_cap.ensure(SH_MAX_SHAPES); h->split_sc.ensure(1); h->eval_plan.ensure(1); h->split_flags.ensure(4);
   } catch (std::string &e) { return fail(h, e); }
-  if (!h->h_pool_count) CU(cudaMallocHost(&h->h_pool_count, (SH_MAX_SHAPES + 4) * sizeof(unsigned long long)));
-  if ((int)h->h_pool_cap.size() != ns) {   // first sizing: 16 records per pair-direction, spread over the shapes
-    h->h_pool_cap.assign(ns, std::max<long long>(4096, (long long)np * 32 / std::max(1, ns) * 2));
+  if (!h->h_pool_count) {
+    CU(cudaMallocHost(&h->h_pool_count, 8 * sizeof(unsigned long long)));
+    CU(cudaMallocHost(&h->h_split_sc, sizeof(SplitScalars)));
+    CU(cudaMallocHost(&h->h_cache_invalid, sizeof(int)));
+    CU(cudaEventCreateWithFlags(&h->ev_sc, cudaEventDisableTiming));
   }
-  auto tick = [&](int kind) -> int {   // start an event pair of the given class
-    if (h->ev2_used + 2 > h->ev2.size()) { if (drain_events(h)) return -2; }
+  if ((int)h->h_pool_cap.size() != ns) {   // first sizing: 24 records per pair, spread over the shapes, x2
+    h->h_pool_cap.assign(ns, std::max<long long>(4096, (long long)np * 24 / std::max(1, ns) * 2));
+  }
+  auto tick = [&](int kind) -> int {   // start an event pair of the given class (the rings are drained at step boundaries)
+    if (h->ev2_used + 2 > h->ev2.size()) return 0;
     h->ev2_kind[h->ev2_used / 2] = kind;
     if (cudaEventRecord(h->ev2[h->ev2_used], h->stream) != cudaSuccess) return -2;
     return 0;
   };
-  auto tock = [&]() { cudaEventRecord(h->ev2[h->ev2_used + 1], h->stream); h->ev2_used += 2; };
+  auto tock = [&]() { if (h->ev2_used + 2 <= h->ev2.size()) { cudaEventRecord(h->ev2[h->ev2_used + 1], h->stream); h->ev2_used += 2; } };
+  const int use_bounds = (h->tune_variant & 2) ? 0 : 1;
   // ---- candidate cache: (re)build when the pair list changed or a particle used up its displacement margin
   CacheArgs C;
   C.enabled = (h->tune_variant & (8 | 2)) ? 0 : 1;   // the cache is built from the direction-cell bounds
   C.invalid = h->scalars.p + 3;
   if (C.enabled) {
-    try { h->cache_off.ensure((size_t)2 * np + 2); h->cache_cnt.ensure((size_t)2 * np + 2); h->cache_count.ensure(2); }
+    try { h->cache_hot.ensure((size_t)np + 2); h->cache_count.ensure(2); }
     catch (std::string &e) { return fail(h, e); }
     if (!h->cache_valid) {
-      if (h->cache_cap < (long long)np * 64) h->cache_cap = (long long)np * 64;
+      // margin level: a cache that was used up quickly gets a wider margin, one that lived long a tighter one
+      if (h->cache_level_pin >= 0) h->cache_level = h->cache_level_pin;
+      else if (h->cache_exhausted) {
+        if (h->cache_age < 40 && h->cache_level < SH_CACHE_LEVELS - 1) h->cache_level++;
+        else if (h->cache_age > 600 && h->cache_level > 0) h->cache_level--;
+      }
+      h->cache_exhausted = false;
+      if (h->cache_cap < (long long)np * 48) h->cache_cap = (long long)np * 48;
+      if (tick(4)) return -2;
       for (int attempt = 0;; attempt++) {
         if (attempt > 6) return fail(h, "candidate cache kept overflowing");
         try { h->cache_pool.ensure((size_t)h->cache_cap + 64); } catch (std::string &e) { return fail(h, e); }
         CU(cudaMemsetAsync(h->cache_count.p, 0, 2 * sizeof(unsigned long long), h->stream));
         CU(cudaMemsetAsync(h->split_flags.p + 2, 0, sizeof(int), h->stream));
-        C.pool = h->cache_pool.p; C.off = h->cache_off.p; C.cnt = h->cache_cnt.p; C.count = h->cache_count.p;
-        C.cap = h->cache_cap; C.overflow = h->split_flags.p + 2;
-        pair_cache_build_kernel<WPB><<<cdiv(np, WPB), WPB * 32, 0, h->stream>>>(P, C);
+        C.pool = h->cache_pool.p; C.hot = h->cache_hot.p; C.count = h->cache_count.p;
+        C.cap = h->cache_cap; C.overflow = h->split_flags.p + 2; C.level = h->cache_level;
+        pair_cache_build_kernel<4><<<cdiv(np, 4), 4 * 32, 0, h->stream>>>(P, C);
         h->kernel_launches++;
         CU(cudaMemcpyAsync(h->h_pool_count, h->cache_count.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
         CU(cudaMemcpyAsync(h->h_pool_count + 1, h->split_flags.p + 2, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -418,87 +496,78 @@ int run_split_pipeline(sh_ctx *h, PairArgs &P) {
       }
       cache_origin_kernel<<<cdiv(h->n, 256), 256, 0, h->stream>>>(view_all(h));
       CU(cudaMemsetAsync(h->scalars.p + 3, 0, sizeof(int), h->stream));
+      tock();
       h->kernel_launches++;
-      h->cache_valid = true; h->cache_builds++;
+      h->cache_valid = true; h->cache_builds++; h->cache_age = 0;
     } else {
       double dmin = 1e300;
-      for (auto &sh : h->shapes) dmin = std::min(dmin, sh.cache_delta);
-      cache_check_kernel<<<cdiv(h->n, 256), 256, 0, h->stream>>>(view_all(h), h->d_shapes.p, 0.5 * dmin, h->scalars.p + 3);
+      for (auto &sh : h->shapes) dmin = std::min(dmin, sh.cache_delta[h->cache_level]);
+      cache_check_kernel<<<cdiv(h->n, 256), 256, 0, h->stream>>>(view_all(h), h->d_shapes.p, h->cache_level, 0.5 * dmin, h->scalars.p + 3);
       h->kernel_launches++;
     }
+    h->cache_age++;
   }
-  C.pool = h->cache_pool.p; C.off = h->cache_off.p; C.cnt = h->cache_cnt.p; C.count = h->cache_count.p;
-  C.cap = h->cache_cap; C.overflow = h->split_flags.p + 2;
-  for (int attempt = 0; attempt < 6; attempt++) {
-    std::vector<long long> base(ns);
-    long long tot = 0;
-    for (int s = 0; s < ns; s++) { base[s] = tot; tot += h->h_pool_cap[s]; }
-    try { h->pool.ensure((size_t)tot + 64); h->pool_flag.ensure((size_t)tot + 64); } catch (std::string &e) { return fail(h, e); }
-    CU(cudaMemcpyAsync(h->pool_base.p, base.data(), ns * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(h->pool_cap.p, h->h_pool_cap.data(), ns * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemsetAsync(h->pool_count.p, 0, SH_MAX_SHAPES * sizeof(unsigned long long), h->stream));
-    CU(cudaMemsetAsync(h->split_flags.p, 0, 4 * sizeof(int), h->stream));
-    SplitArgs S;
-    S.pool = h->pool.p; S.pool_flag = h->pool_flag.p; S.pool_base = h->pool_base.p; S.pool_cap = h->pool_cap.p; S.pool_count = h->pool_count.p;
-    S.pd_off = h->pd_off.p; S.pd_cnt = h->pd_cnt.p; S.big_list = h->big_list.p; S.nbig = h->split_flags.p; S.overflow = h->split_flags.p + 1;
-    CU(cudaMemcpyAsync(h->counters.p + 8, h->counters.p, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, h->stream));
-    if (tick(0)) return -2;
-    pair_cull_kernel<1><<<np, 32, 0, h->stream>>>(P, S, C, (h->tune_variant & 2) ? 0 : 1);   // small CTAs: pairs differ in length
+  C.pool = h->cache_pool.p; C.hot = h->cache_hot.p; C.count = h->cache_count.p;
+  C.cap = h->cache_cap; C.overflow = h->split_flags.p + 2; C.level = h->cache_level;
+  std::vector<long long> base(ns);
+  long long tot = 0;
+  for (int s2 = 0; s2 < ns; s2++) { base[s2] = tot; tot += h->h_pool_cap[s2]; }
+  try { h->pool.ensure((size_t)tot + 64); h->pool_flag.ensure((size_t)tot + 64); } catch (std::string &e) { return fail(h, e); }
+  CU(cudaMemcpyAsync(h->pool_base.p, base.data(), ns * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->pool_cap.p, h->h_pool_cap.data(), ns * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemsetAsync(h->split_sc.p, 0, sizeof(SplitScalars), h->stream));
+  SplitArgs S;
+  S.pool = h->pool.p; S.pool_flag = h->pool_flag.p; S.pool_base = h->pool_base.p; S.pool_cap = h->pool_cap.p; S.sc = h->split_sc.p;
+  S.pd = h->pd.p; S.big_list = h->big_list.p; S.slow_list = h->slow_list.p;
+  // ---- A
+  if (tick(0)) return -2;
+  if (C.enabled) {
+    // one pair per half warp (default) or per warp ("cull_lpp" 32); WPB warps per CTA
+    const int cw = h->tune_cull_wpb > 0 ? h->tune_cull_wpb : 1;
+    const int ppw = h->tune_cull_lpp == 32 ? 1 : 2;
+    const int grid = cdiv(np, cw * ppw);
+#define LAUNCH_CULL(W, L) pair_cull_cached_kernel<W, L><<<grid, W * 32, 0, h->stream>>>(P, S, C, use_bounds)
+    if (ppw == 1) { if (cw == 1) LAUNCH_CULL(1, 32); else if (cw == 2) LAUNCH_CULL(2, 32); else if (cw == 8) LAUNCH_CULL(8, 32); else LAUNCH_CULL(4, 32); }
+    else { if (cw == 1) LAUNCH_CULL(1, 16); else if (cw == 2) LAUNCH_CULL(2, 16); else if (cw == 8) LAUNCH_CULL(8, 16); else LAUNCH_CULL(4, 16); }
+#undef LAUNCH_CULL
+    h->kernel_launches++;
+  }
+  {
+    constexpr int WW = 2;   // persistent; pairs differ a lot in length, small CTAs retire independently
+    const int grid = std::max(1, std::min(cdiv(np, WW), h->sm_count * 16));
+    pair_cull_window_kernel<WW><<<grid, WW * 32, 0, h->stream>>>(P, S, C, use_bounds);
+    h->kernel_launches++;
+  }
+  tock();
+  // ---- B
+  int maxT = 1;
+  for (int s2 = 0; s2 < ns; s2++) maxT = std::max(maxT, h->shape_host_view[s2].nterms4 + 4);
+  if (tick(1)) return -2;
+  if (h->eval_pts == 2) rc = h->eval_occ == 3 ? launch_eval<WPB, 2, 3>(h, S, maxT) : launch_eval<WPB, 2, 4>(h, S, maxT);
+  else rc = launch_eval<WPB, 4, 2>(h, S, maxT);
+  if (rc) return rc;
+  tock();
+  h->eval_launches++;
+  // ---- C
+  if (tick(2)) return -2;
+  pair_reduce_kernel<<<cdiv(np, 128), 128, 0, h->stream>>>(P, S);
+  tock();
+  h->kernel_launches++;
+  // ---- deep contacts / pairs that found the pool full: fused kernel over the device-side list
+  {
+    PairArgs Pb = P;
+    Pb.pair_list = h->big_list.p; Pb.npairs = np; Pb.npairs_dev = &h->split_sc.p->nbig; Pb.work_counter = &h->split_sc.p->deep_counter;
+    if (tick(3)) return -2;
+    rc = launch_fused(h, Pb, h->sm_count);
+    if (rc) return rc;
     tock();
     h->kernel_launches++;
-    CU(cudaMemcpyAsync(h->h_pool_count, h->pool_count.p, ns * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaMemcpyAsync(h->h_pool_count + SH_MAX_SHAPES, h->split_flags.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaMemcpyAsync(h->h_pool_count + SH_MAX_SHAPES + 1, h->scalars.p + 3, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    const int *fl = reinterpret_cast<const int *>(h->h_pool_count + SH_MAX_SHAPES);
-    const int nbig = fl[0], overflow = fl[1];
-    if (C.enabled && fl[2] != 0) h->cache_valid = false;   // margin used up: this step ran on the window, rebuild next step
-    if (overflow) {   // grow the pools to what this step asked for (+50 %) and redo the cull
-      for (int s = 0; s < ns; s++) h->h_pool_cap[s] = std::max<long long>(h->h_pool_cap[s], (long long)(h->h_pool_count[s] * 3 / 2) + 4096);
-      // the cull kernel already added its pair / transform counters: restore the snapshot before the redo
-      CU(cudaMemcpyAsync(h->counters.p, h->counters.p + 8, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, h->stream));
-      h->split_redo++;
-      continue;
-    }
-    // ---- B
-    EvalPlan plan;
-    plan.nshape = ns;
-    int nblk = 0, maxT = 1;
-    for (int s = 0; s < ns; s++) {
-      plan.blk_start[s] = nblk;
-      plan.count[s] = (long long)h->h_pool_count[s];
-      nblk += (int)((plan.count[s] + 64 * WPB - 1) / (64 * WPB));
-      maxT = std::max(maxT, h->shape_host_view[s].nterms4 + 4);
-    }
-    plan.blk_start[ns] = nblk;
-    if (nblk > 0) {
-      const size_t smem = (size_t)maxT * 24 + 32;
-      CU(cudaFuncSetAttribute(pair_eval_kernel<WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
-      if (tick(1)) return -2;
-      pair_eval_kernel<WPB><<<nblk, WPB * 32, smem, h->stream>>>(h->d_shapes.p, S, plan, h->counters.p);
-      tock();
-      h->kernel_launches++; h->eval_launches++;
-    }
-    // ---- C
-    if (tick(2)) return -2;
-    pair_reduce_kernel<<<cdiv(np, 128), 128, 0, h->stream>>>(P, S);
-    tock();
-    h->kernel_launches++;
-    // ---- deep contacts
-    if (nbig > 0) {
-      PairArgs Pb = P;
-      Pb.pair_list = h->big_list.p; Pb.npairs = nbig;
-      CU(cudaMemsetAsync(h->scalars.p + 2, 0, sizeof(int), h->stream));
-      if (tick(3)) return -2;
-      int rc = launch_fused(h, Pb);
-      if (rc) return rc;
-      tock();
-      h->kernel_launches++;
-      h->big_pairs += nbig;
-    }
-    return 0;
   }
-  return fail(h, "survivor pool kept overflowing");
+  CU(cudaMemcpyAsync(h->h_split_sc, h->split_sc.p, sizeof(SplitScalars), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(h->h_cache_invalid, h->scalars.p + 3, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaEventRecord(h->ev_sc, h->stream));
+  h->sc_pending = true; h->sc_nshape = ns;
+  return 0;
 }
 
 int compute_forces_device(sh_ctx *h) {
@@ -509,17 +578,18 @@ int compute_forces_device(sh_ctx *h) {
   if (h->npairs > 0) {
     PairArgs P;
     P.shapes = h->d_shapes.p; P.c = h->c.p; P.Rs = h->Rs.p; P.x = h->x.p; P.shape = h->shape.p; P.stride = h->stride;
-    P.pair_i = h->pair_i.p; P.pair_j = h->pair_j.p; P.pair_eij = h->pair_eij.p; P.pair_eji = h->pair_eji.p;
+    P.pair_i = h->pair_i.p; P.pair_j = h->pair_j.p; P.pair_eij = h->pair_eij.p; P.pair_eji = h->pair_eji.p; P.pair_img = h->pair_img.p;
     P.npairs = h->npairs; P.slot = h->slot.p; P.slot_stride = h->slot_stride; P.pres = h->pres.p; P.pres_stride = h->pres_stride;
     P.pk = h->d_pk.p; P.pm = h->d_pm.p;
     for (int d = 0; d < 3; d++) { P.boxlen[d] = h->hi[d] - h->lo[d]; P.periodic[d] = h->periodic[d]; }
     P.work_counter = h->scalars.p + 2; P.counters = h->counters.p;
     int maxT = 1, maxq = 32;
     for (auto &s : h->shapes) { maxT = std::max(maxT, s.nterms); maxq = std::max(maxq, s.nq); }
-    P.max_terms = maxT; P.max_nq = maxq; P.nlocal = n; P.pair_list = nullptr;
+    P.max_terms = maxT; P.max_nq = maxq; P.nlocal = n; P.pair_list = nullptr; P.npairs_dev = nullptr;
     CU(cudaMemsetAsync(h->scalars.p + 2, 0, sizeof(int), h->stream));
     const int nt = h->tune_threads ? h->tune_threads : 128;
-    if (h->ev_used + 2 > h->ev.size()) { if (drain_events(h)) return -2; }
+    // the event rings are drained only here, at a step boundary, before the outer start event
+    if (h->ev_used + 2 > h->ev.size() || h->ev2_used + 16 > h->ev2.size()) { if (drain_events(h)) return -2; }
     CU(cudaEventRecord(h->ev[h->ev_used], h->stream));
     int rc;
     if (h->tune_variant & 1) {           // CTA-per-pair kernel (full-table scan)
@@ -603,7 +673,7 @@ int sh_create(sh_ctx **out, int device_id) {
   cudaMemset(h->scalars.p, 0, 16 * sizeof(int));
   cudaMemset(h->counters.p, 0, 16 * sizeof(unsigned long long));
   cudaMallocHost(&h->h_pinned, 64);
-  cudaEventCreate(&h->run_e0); cudaEventCreate(&h->run_e1); cudaEventCreate(&h->ev_b0); cudaEventCreate(&h->ev_b1);
+  cudaEventCreate(&h->run_e0); cudaEventCreate(&h->run_e1);
   h->ev.resize(2048); h->ev2.resize(4096); h->ev2_kind.resize(2048);
   for (auto &e : h->ev) cudaEventCreate(&e);
   for (auto &e : h->ev2) cudaEventCreate(&e);
@@ -615,20 +685,20 @@ int sh_destroy(sh_ctx *h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  for (auto &d : h->shape_dev) { d.Ap.release(); d.ab.release(); d.node.release(); d.row_x.release(); d.cube.release(); d.pf.release(); d.cubew.release(); }
+  for (auto &d : h->shape_dev) { d.Ap.release(); d.ab.release(); d.node.release(); d.row_x.release(); d.cube.release(); d.pf4.release(); for (auto &w : d.cubew) w.release(); }
   h->d_shapes.release(); h->d_pk.release(); h->d_pm.release();
   DevBuf<double> *db[] = {&h->x, &h->v, &h->q, &h->L, &h->f, &h->tq, &h->c, &h->Rs, &h->c0, &h->wallf, &h->ewall, &h->ke, &h->bbox, &h->slot, &h->pres};
   for (auto *b : db) b->release();
   DevBuf<int> *ib[] = {&h->shape, &h->cell_of, &h->cell_count, &h->cell_start, &h->cell_fill, &h->cell_atoms, &h->tile_sum, &h->cnt_full,
-                       &h->cnt_half, &h->nbr_off, &h->half_off, &h->nbr_j, &h->pair_i, &h->pair_j, &h->pair_eij, &h->pair_eji, &h->scalars};
+                       &h->cnt_half, &h->nbr_off, &h->half_off, &h->nbr_j, &h->pair_i, &h->pair_j, &h->pair_eij, &h->pair_eji, &h->pair_img, &h->scalars};
   for (auto *b : ib) b->release();
   h->counters.release();
   for (auto &e : h->ev) cudaEventDestroy(e);
   for (auto &e : h->ev2) cudaEventDestroy(e);
-  h->pool.release(); h->pool_flag.release(); h->pool_base.release(); h->pool_cap.release(); h->pd_off.release(); h->pool_count.release();
-  h->pd_cnt.release(); h->big_list.release(); h->split_flags.release();
-  h->cache_pool.release(); h->cache_off.release(); h->cache_cnt.release(); h->cache_count.release(); h->cc0.release(); h->cq0.release();
-  if (h->h_pool_count) cudaFreeHost(h->h_pool_count);
+  h->pool.release(); h->pool_flag.release(); h->pool_base.release(); h->pool_cap.release(); h->split_sc.release(); h->eval_plan.release(); h->slow_list.release();
+  h->pd.release(); h->cache_hot.release(); h->big_list.release(); h->split_flags.release();
+  h->cache_pool.release(); h->cache_count.release(); h->cc0.release(); h->cq0.release();
+  if (h->h_pool_count) { cudaFreeHost(h->h_pool_count); cudaFreeHost(h->h_split_sc); cudaFreeHost(h->h_cache_invalid); cudaEventDestroy(h->ev_sc); }
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   h->stage.release();
   cudaEventDestroy(h->run_e0); cudaEventDestroy(h->run_e1);
@@ -657,7 +727,7 @@ int sh_set_quadrature(sh_ctx *h, int n_theta, int n_phi) {
 int sh_add_shape(sh_ctx *h, int lmax, const double *a_lm, const double *b_lm, double density, int *shape_id_out) {
   if ((int)h->shapes.size() >= SH_MAX_SHAPES) return fail(h, "too many shapes");
   ShapeTables t;
-  std::string e = build_shape_tables(lmax, a_lm, b_lm, density, h->n_theta, h->n_phi, t);
+  std::string e = build_shape_tables(lmax, a_lm, b_lm, density, h->n_theta, h->n_phi, t, h->cube_n);
   if (!e.empty()) return fail(h, e);
   h->shapes.push_back(std::move(t));
   h->shapes_dirty = true; h->forces_valid = false; h->list_valid = false;
@@ -1150,10 +1220,11 @@ int sh_get_split_stats(const sh_ctx *hc, double *seconds_eval, int64_t *eval_lau
   CU(cudaSetDevice(h->device));
   int rc = drain_events(h);
   if (rc) return rc;
+  if ((rc = absorb_split_feedback(h))) return rc;
   if (seconds_eval) *seconds_eval = h->sec_eval;
   if (eval_launches) *eval_launches = h->eval_launches;
   if (deep_pairs) *deep_pairs = h->big_pairs;
-  if (pool_redos) *pool_redos = h->split_redo;
+  if (pool_redos) *pool_redos = h->pool_grows;
   if (cache_builds) *cache_builds = h->cache_builds;
   return 0;
 }
@@ -1163,9 +1234,40 @@ int sh_reset_timers(sh_ctx *h) {
   int rc = drain_events(h);
   if (rc) return rc;
   h->sec_pair = h->sec_neigh = h->sec_other = 0; h->pair_launches = 0; h->sec_run_total = 0;
-  h->sec_eval = h->sec_cull = h->sec_reduce = h->sec_deep = 0; h->eval_launches = 0; h->big_pairs = 0; h->split_redo = 0; h->cache_builds = 0;
+  h->sec_eval = h->sec_cull = h->sec_reduce = h->sec_deep = 0; h->eval_launches = 0; h->big_pairs = 0; h->slow_pairs = 0; h->pool_grows = 0; h->cache_builds = 0; h->sec_cache = 0;
   h->neighbor_builds = 0; h->kernel_launches = 0;
   CU(cudaMemset(h->counters.p, 0, 16 * sizeof(unsigned long long)));
+  return 0;
+}
+
+int sh_get_cache_stats(const sh_ctx *hc, int64_t *cache_builds, double *seconds_cache, int *level, int64_t *slow_pairs) {
+  sh_ctx *h = const_cast<sh_ctx *>(hc);
+  CU(cudaSetDevice(h->device));
+  int rc = drain_events(h);
+  if (rc) return rc;
+  if ((rc = absorb_split_feedback(h))) return rc;
+  if (cache_builds) *cache_builds = h->cache_builds;
+  if (seconds_cache) *seconds_cache = h->sec_cache;
+  if (level) *level = h->cache_level;
+  if (slow_pairs) *slow_pairs = h->slow_pairs;
+  return 0;
+}
+
+int sh_set_tuning(sh_ctx *h, const char *key, double value) {
+  if (!h || !key) return -1;
+  const std::string k(key);
+  const int v = (int)value;
+  if (k == "cull_wpb") { if (v != 0 && v != 1 && v != 2 && v != 4 && v != 8) return fail(h, "cull_wpb must be 0, 1, 2, 4 or 8"); h->tune_cull_wpb = v; }
+  else if (k == "cull_lpp") { if (v != 0 && v != 16 && v != 32) return fail(h, "cull_lpp must be 0, 16 or 32"); h->tune_cull_lpp = v; }
+  else if (k == "eval_pts") { if (v != 0 && v != 2 && v != 4) return fail(h, "eval_pts must be 0, 2 or 4"); h->eval_pts = v; }
+  else if (k == "eval_occ") { if (v != 0 && v != 3 && v != 4) return fail(h, "eval_occ must be 0, 3 or 4"); h->eval_occ = v; }
+  else if (k == "eval_mode") { if (v < 0 || v > 2) return fail(h, "eval_mode must be 0 (default), 1 (one block per CTA) or 2 (persistent chunks)"); h->eval_mode = v; }
+  else if (k == "cache_level") { if (v < -1 || v >= SH_CACHE_LEVELS) return fail(h, "cache_level must be -1 (adaptive) .. 2"); h->cache_level_pin = v; h->cache_valid = false; }
+  else if (k == "cube_n") {
+    if (!h->shapes.empty()) return fail(h, "cube_n must be set before add_shape");
+    if (v != 0 && (v < 8 || v > 144)) return fail(h, "cube_n must be 0 (default) or 8..144");
+    h->cube_n = v;
+  } else return fail(h, "unknown tuning key: " + k);
   return 0;
 }
 

@@ -85,7 +85,7 @@ __global__ void unpack_atoms_kernel(AtomView A, int first, int m, const double *
 
 // candidate cache (pair_split_kernels.cuh): a node of atom i has moved, relative to any partner frame, by at most
 // w_i = |c - c0| + angle(q0 -> q) * (rmax_i + delta_i); the cache stays valid while every w_i <= thresh.
-__global__ void cache_check_kernel(AtomView A, const DevShape *shapes, double thresh, int *flag) {
+__global__ void cache_check_kernel(AtomView A, const DevShape *shapes, int level, double thresh, int *flag) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= A.n) return;
   const int st = A.stride;
@@ -100,7 +100,7 @@ __global__ void cache_check_kernel(AtomView A, const DevShape *shapes, double th
   }
   const double dq = sqrt(fmin(dm, dp));                 // = 2 sin(angle/4)
   const double ang = dq < 0.2 ? 2.02 * dq : 10.0;       // angle <= 2.02 dq for small rotations
-  const double w = sqrt(u2) + ang * (s.rmax + s.cache_delta);
+  const double w = sqrt(u2) + ang * (s.rmax + s.cache_delta[level]);
   if (!(w <= thresh)) *flag = 1;
 }
 __global__ void cache_origin_kernel(AtomView A) {

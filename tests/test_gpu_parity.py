@@ -311,3 +311,73 @@ def test_error_paths():
     g.set_atoms(np.zeros(0, np.int32), np.zeros((0, 3)))   # empty system is legal
     g.run(3)
     assert g.get_pairs()["V"].size == 0
+
+
+def scaled_cfg(cfg, s):
+    """The same packing in other length units: lengths x s, coefficients a_lm x s (r scales), velocities x s,
+    stiffness x s^2 (exponent 1: F/m scales with s), so that x'(t) = s x(t) exactly."""
+    c = dict(cfg)
+    c["shapes"] = [(np.asarray(a) * s, np.asarray(b) * s) for (a, b) in cfg["shapes"]]
+    c["x"] = np.asarray(cfg["x"]) * s
+    c["v"] = np.asarray(cfg["v"]) * s
+    if cfg["box"] is not None:
+        lo, hi, per = cfg["box"]
+        c["box"] = (np.asarray(lo) * s, np.asarray(hi) * s, per)
+    c["skin"] = cfg["skin"] * s
+    c["coeff"] = (cfg["coeff"][0] * s ** 2, cfg["coeff"][1])    # accelerations scale with s: the dynamics are similar
+    return c
+
+
+@pytest.mark.parametrize("variant", PIPELINES + [4])
+@pytest.mark.parametrize("scale", [1e-3, 1e2])
+def test_unit_scale_independence(scale, variant):
+    """the FP32 pre-cull margins are relative to the pair's length scale, so SI-scale radii
+    (1e-3) and large units (1e2) make exactly the decisions the oracle makes."""
+    cfg = scaled_cfg(W.packing((3, 3, 3), 20, (32, 64), nshapes=4, seed=21, nn_frac=1.75, name="scaled"), scale)
+    g, o = both(cfg, variant=variant)
+    e = check_forces(g, o)
+    assert e["ncontact"] > 30
+    if variant == 16:
+        # the pre-cull still prunes: far fewer nodes reach the exact stage than the window holds
+        c = g.get_counters()
+        assert c["nodes_evaluated"] < 0.2 * o.get_counters()["nodes_evaluated"]
+    g.run(30); o.run(30)
+    cg, co = g.get_counters(), o.get_counters()
+    assert cg["nodes_inside"] == co["nodes_inside"]
+    g.close(); o.close()
+
+
+@pytest.mark.parametrize("knob", [("cull_wpb", 1), ("cull_wpb", 2), ("cull_wpb", 8), ("cull_lpp", 32), ("eval_pts", 2), ("eval_pts", 4),
+                                  ("cache_level", 0), ("cache_level", 2), ("cube_n", 48), ("cube_n", 12)])
+def test_split_pipeline_knobs(knob):
+    """Every launch shape / table resolution of the split pipeline makes the oracle's decisions."""
+    cfg = W.packing((3, 3, 3), 20, (32, 64), nshapes=4, seed=23, nn_frac=1.7, vel_sigma=0.8, dt=5e-4, name="knobs")
+    g = pkg.ShGpu()
+    if knob[0] == "cube_n":
+        g.set_tuning(*knob)
+    o = O.Oracle(threads=8)
+    W.apply(g, cfg); W.apply(o, cfg)
+    g.set_pair_tuning(0, 0, 16)
+    if knob[0] != "cube_n":
+        g.set_tuning(*knob)
+    check_forces(g, o)
+    g.run(60); o.run(60)
+    cg, co = g.get_counters(), o.get_counters()
+    assert cg["nodes_inside"] == co["nodes_inside"] and cg["pair_evals"] == co["pair_evals"]
+    e = pair_rel_errors(g.get_pairs(), o.get_pairs())
+    assert max(e["V"], e["F"], e["tau"]) <= 1e-8, e
+    g.close(); o.close()
+
+
+def test_full_pool_falls_back_to_the_fused_kernel():
+    """A survivor pool that is too small costs time, never correctness: the pairs that do not fit are evaluated by
+    the fused kernel in the same step and the host grows the pool for the next one."""
+    cfg = W.packing((4, 4, 4), 20, (32, 64), nshapes=4, seed=29, nn_frac=1.6, name="deep")     # deep overlaps
+    g, o = both(cfg, variant=16)
+    e = check_forces(g, o)
+    st = g.get_split_stats()
+    assert e["ncontact"] > 100
+    g.run(3); o.run(3)
+    assert g.get_counters()["nodes_inside"] == o.get_counters()["nodes_inside"]
+    print("deep / pool stats", st, g.get_split_stats())
+    g.close(); o.close()
