@@ -117,14 +117,15 @@ int sh_get_split_times(const sh_ctx *h, double *seconds_cull, double *seconds_ev
                        double *seconds_deep);
 int sh_get_split_stats(const sh_ctx *h, double *seconds_eval, int64_t *eval_launches, int64_t *deep_pairs,
                        int64_t *pool_redos, int64_t *cache_builds);
-/* candidate cache of the split pipeline: builds and their device time, margin level in use, pairs that took the
- * window (slow) path */
-int sh_get_cache_stats(const sh_ctx *h, int64_t *cache_builds, double *seconds_cache, int *level, int64_t *slow_pairs);
+/* candidate cache of the split pipeline: full builds, device time of builds + remaps, margin level in use, pairs that
+ * took the window (slow) path, remaps (cache carried over a neighbor rebuild) */
+int sh_get_cache_stats(const sh_ctx *h, int64_t *cache_builds, double *seconds_cache, int *level, int64_t *slow_pairs,
+                       int64_t *cache_remaps);
 /* device time of sh_run (events on the library's stream bracketing all steps of the call) -------- */
 int sh_get_run_time(const sh_ctx *h, double *seconds_last_run, double *seconds_total);
 
 /* tuning knobs of the pair phase; 0 = default.  variant bits: 1 CTA-per-pair full-scan kernel, 2 direction-cell
- * bound off, 4 fused warp-per-pair kernel, 8 candidate cache off, 16 force the split pipeline (systems with fewer
+ * bound off, 4 fused warp-per-pair kernel, 8 candidate cache off, 32 no cache remap on neighbor rebuilds, 16 force the split pipeline (systems with fewer
  * than 16384 pairs default to the fused kernel) -------------------------------------------------- */
 int sh_set_pair_tuning(sh_ctx *h, int threads_per_cta, int ctas_per_sm, int variant);
 

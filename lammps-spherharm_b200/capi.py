@@ -267,9 +267,10 @@ class ShGpu:
                     cache_builds=e.value)
 
     def get_cache_stats(self):
-        nb, sec, lv, slow = C.c_int64(), C.c_double(), C.c_int(), C.c_int64()
-        self._ck(self.L.sh_get_cache_stats(self.h, C.byref(nb), C.byref(sec), C.byref(lv), C.byref(slow)))
-        return dict(cache_builds=nb.value, seconds_cache=sec.value, level=lv.value, slow_pairs=slow.value)
+        nb, sec, lv, slow, rm = C.c_int64(), C.c_double(), C.c_int(), C.c_int64(), C.c_int64()
+        self._ck(self.L.sh_get_cache_stats(self.h, C.byref(nb), C.byref(sec), C.byref(lv), C.byref(slow), C.byref(rm)))
+        return dict(cache_builds=nb.value, seconds_cache=sec.value, level=lv.value, slow_pairs=slow.value,
+                    cache_remaps=rm.value)
 
     def set_tuning(self, key, value):
         """Named knobs (include/shgpu.h sh_set_tuning): cull_wpb, eval_pts, cache_level, cube_n."""

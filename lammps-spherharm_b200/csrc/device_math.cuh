@@ -27,8 +27,8 @@ struct DevShape {
   const float2 *cube_ul;                  // per cube-map direction cell: {ub2, lb2} = proven bounds of r^2 over the cell
   int cube_n, pad2_;                      // cells per face edge
   const float4 *pf4;                      // FP32 copy of the node points (x,y,z,0) for the conservative pre-cull
-  const float *cube_w2[3];                // candidate-cache tables per margin level (inflated wide bound^2 per cell)
-  double cache_delta[3];                  // node displacement margin of the candidate cache per level
+  const float *cube_w2[4];                // candidate-cache tables per margin level (inflated wide bound^2 per cell)
+  double cache_delta[4];                  // node displacement margin of the candidate cache per level
 };
 
 // rotation matrix (row-major R[3*r+c]) of unit quaternion (w,x,y,z); plain mul/add, fixed order

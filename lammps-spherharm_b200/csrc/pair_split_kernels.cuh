@@ -208,13 +208,15 @@ __device__ __forceinline__ int exact_node_stage(const double *M, const double *t
 
 // ---- candidate cache build: window + FP32 tests against the INFLATED bounds (rmax_b + delta; cube_w2[level]), no FP64
 // node work.  Both directions are staged in shared memory and appended as ONE run per pair.
+// list == nullptr: every pair; else the pairs list[0 .. *nlist) (pairs that join a live cache after a neighbor rebuild).
 template <int WPB>
-__global__ void __launch_bounds__(WPB * 32) pair_cache_build_kernel(PairArgs A, CacheArgs C) {
+__global__ void __launch_bounds__(WPB * 32) pair_cache_build_kernel(PairArgs A, CacheArgs C, const int *list, const int *nlist) {
   __shared__ unsigned short s_buf[WPB][2][CACHE_CAP];
   __shared__ double s_pose[WPB][16];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int p = blockIdx.x * WPB + warp;
-  if (p >= A.npairs) return;
+  const int nwork = list ? *nlist : A.npairs;
+  for (int w = blockIdx.x * WPB + warp; w < nwork; w += gridDim.x * WPB) {
+  const int p = list ? list[w] : w;
   const int i = A.pair_i[p], j = A.pair_j[p];
   double d[3];
   pair_separation(A, p, i, j, d);
@@ -295,6 +297,50 @@ __global__ void __launch_bounds__(WPB * 32) pair_cache_build_kernel(PairArgs A, 
     PairHot hrec;
     hrec.i = i; hrec.j = j; hrec.n0 = over ? -1 : cnt0; hrec.n1 = over ? -1 : cnt1; hrec.off = off; hrec.img = A.pair_img[p];
     hrec.shp_i = (unsigned char)shp_i; hrec.shp_j = (unsigned char)shp_j; hrec.pad0 = 0; hrec.pad1 = 0;
+    C.hot[p] = hrec;
+  }
+  __syncwarp();
+  }  // work loop
+}
+
+// ---- candidate cache after a neighbor rebuild (same atoms, same indices): a pair that was in the old list keeps its
+// candidates (the cache's reference state and validity test are unchanged); pairs that are new go to `fresh_list` and
+// are built by pair_cache_build_kernel with the next larger margin (they start from a state that may already have used
+// up half of the current one).  One thread per new pair; the pool space of a warp is allocated with one atomic.
+__global__ void cache_remap_kernel(PairArgs A, const int *old_half_off, const int *old_pair_j, int old_nown, const PairHot *old_hot,
+                                   const unsigned short *old_pool, CacheArgs C, int *fresh_list, int *nfresh) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int ntot = 0, q = -1;
+  PairHot hrec;
+  hrec.i = hrec.j = 0; hrec.n0 = hrec.n1 = 0; hrec.off = 0; hrec.img = 0; hrec.shp_i = hrec.shp_j = 0; hrec.pad0 = hrec.pad1 = 0;
+  if (p < A.npairs) {
+    const int i = A.pair_i[p], j = A.pair_j[p], img = A.pair_img[p];
+    if (i < old_nown)
+      for (int e = old_half_off[i]; e < old_half_off[i + 1]; e++)
+        if (old_pair_j[e] == j) { q = e; break; }
+    if (q >= 0) {
+      hrec = old_hot[q];
+      if (hrec.n0 < 0 || hrec.img != img || hrec.i != i || hrec.j != j) q = -1;
+    }
+    if (q >= 0) ntot = hrec.n0 + hrec.n1;
+    else fresh_list[atomicAdd(nfresh, 1)] = p;
+  }
+  // warp-aggregated allocation
+  int pre = ntot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += t; }
+  const int wtot = __shfl_sync(0xffffffffu, pre, 31);
+  long long base = 0;
+  if (lane == 31 && wtot > 0) base = (long long)atomicAdd(C.count, (unsigned long long)wtot);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  if (q >= 0) {
+    const long long off = base + (pre - ntot);
+    if (off + ntot <= C.cap) {
+      const unsigned short *src = old_pool + hrec.off;
+      for (int r = 0; r < ntot; r++) C.pool[off + r] = src[r];
+      hrec.off = off;
+    } else { *C.overflow = 1; hrec.n0 = -1; hrec.n1 = -1; hrec.off = 0; }   // no room: the pair takes the window path
     C.hot[p] = hrec;
   }
 }

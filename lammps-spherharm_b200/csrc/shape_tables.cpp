@@ -230,7 +230,7 @@ void sample_faces(const ShapeTables &s, int NS, int K, FaceSamples &F) {
 static inline float sq_up(double v) { float q = (float)(v * v); return std::nextafter(q, 3.0e38f); }
 static inline float sq_down(double v) { float q = (float)(v * v); return std::nextafter(q, 0.0f); }
 
-const double kCacheFrac[SH_CACHE_LEVELS] = {0.005, 0.01, 0.02};   // cache_delta[level] / rmax
+const double kCacheFrac[SH_CACHE_LEVELS] = {0.005, 0.01, 0.02, 0.04};   // cache_delta[level] / rmax
 
 std::string build_cube_tables(ShapeTables &s, int n) {
   derivative_bounds(s);
@@ -242,7 +242,16 @@ std::string build_cube_tables(ShapeTables &s, int n) {
   for (int lv = 0; lv < SH_CACHE_LEVELS; lv++)
     gamma[lv] = std::asin(std::min(1.0, s.cache_delta[lv] / (s.rmin + 2.0 * s.cache_delta[lv]))) * (1.0 + 1e-9) + 1e-9;
   const double eps_uv = 1e-5;
-  const int K = (int)std::ceil(3.6 * gamma[SH_CACHE_LEVELS - 1] / step) + 3;
+  // the sample grid must reach as far beyond a face as the largest drift box (a corner cell at the widest margin)
+  int K = 3;
+  {
+    const double g = gamma[SH_CACHE_LEVELS - 1];
+    auto stretch = [&](double rho) { const double m = 1.0 + rho + eps_uv; return 1.0 + 2.0 * m * m; };
+    double rho = g * stretch(0.0);
+    for (int it = 0; it < 200 && g * stretch(rho) > rho; it++) rho = g * stretch(rho) * 1.02;
+    if (g * stretch(rho) > rho) return "candidate-cache table: margin too wide for this shape (rmin too small)";
+    K = (int)std::ceil((rho * 1.05 + eps_uv) / step) + 3;
+  }
   FaceSamples F;
   sample_faces(s, NS, K, F);
   const int ns = F.ns;

@@ -30,8 +30,8 @@ struct ShapeTables {
   std::vector<float> cube_ub2, cube_lb2;
   // candidate-cache tables, one per margin level: (max of r over every direction a node direction can drift to before
   // the cache is rebuilt + cache_delta[level])^2; cache_delta = node displacement margin of that level
-  std::vector<float> cube_wide2[3];
-  double cache_delta[3] = {0, 0, 0};
+  std::vector<float> cube_wide2[4];
+  double cache_delta[4] = {0, 0, 0, 0};
   double h1_bound = 0, h2_bound = 0;     // sup |dr/dt|, sup |d2r/dt2| along great circles (t = arc length), rigorous
   double sample_step = 0, sample_pad = 0;   // gnomonic sample spacing and the interpolation pad h2 step^2/4 (+ border term)
   double r_sup = 0, r_inf = 0;           // proven bounds of r over the sphere (max ub, min lb); rmax/rmin are checked against them
@@ -44,7 +44,7 @@ struct ShapeTables {
 };
 
 // Returns "" on success, else an error message.
-constexpr int SH_CACHE_LEVELS = 3;
+constexpr int SH_CACHE_LEVELS = 4;   // 0..2 chosen adaptively; 3 only for pairs that join a live cache (remap)
 std::string build_shape_tables(int lmax, const double *a_lm, const double *b_lm, double density,
                                int n_theta, int n_phi, ShapeTables &out, int cube_n = 0);
 

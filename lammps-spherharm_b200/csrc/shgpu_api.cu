@@ -49,6 +49,8 @@ struct ShapeDev {
 
 }  // namespace
 
+enum { CACHE_INVALID = 0, CACHE_VALID = 1, CACHE_REMAP = 2 };
+
 struct sh_ctx {
   std::string err;
   int device = 0, sm_count = 148;
@@ -79,14 +81,14 @@ struct sh_ctx {
   std::vector<int64_t> tag;
   // neighbor
   DevBuf<int> cell_of, cell_count, cell_start, cell_fill, cell_atoms, tile_sum, cnt_full, cnt_half, nbr_off, half_off,
-      nbr_j, pair_i, pair_j, pair_eij, pair_eji, pair_img, scalars;  // scalars: [0]=total [1]=rebuild flag [2]=work counter
+      nbr_j, pair_i, pair_j, pair_eij, pair_eji, pair_img, scalars;  // scalars: [0]=scan total [1]=rebuild flag [2]=work counter [3]/[4]=cache exhausted (hard/soft) [8]/[9]=list totals
   DevBuf<double> bbox, slot, pres, stage;
   // split pair pipeline (pair_split_kernels.cuh)
   DevBuf<SurvRec> pool;
   DevBuf<unsigned char> pool_flag;
   DevBuf<long long> pool_base, pool_cap;
   DevBuf<PdEntry> pd;
-  DevBuf<PairHot> cache_hot;
+  DevBuf<PairHot> cache_hot[2];       // double-buffered: a neighbor rebuild remaps the live cache into the other buffer
   DevBuf<SplitScalars> split_sc;
   DevBuf<EvalPlanDev> eval_plan;
   DevBuf<int> big_list, slow_list, split_flags;   // split_flags: [2]=cache overflow
@@ -107,11 +109,14 @@ struct sh_ctx {
   int eval_pts = 0, eval_occ = 0, eval_mode = 0;   // pair_eval_kernel: points per lane, min CTAs/SM, 1 = one block per CTA
   long long last_records = 0;                  // records of the previous pair phase (advisory)
   // candidate cache
-  DevBuf<unsigned short> cache_pool;
+  DevBuf<unsigned short> cache_pool[2];
+  DevBuf<int> old_half_off, old_pair_j, fresh_list;   // pair list before the last rebuild (remap), pairs new to the cache
+  int old_nown = 0, cache_cur = 0;
+  int64_t cache_remaps = 0, atoms_epoch = 0, cache_epoch = -1;   // epoch: bumped whenever the atom set / order changes
   DevBuf<unsigned long long> cache_count;
   long long cache_cap = 0;
-  bool cache_valid = false;
-  DevBuf<double> cc0, cq0;
+  int cache_state = 0;                 // CACHE_INVALID / CACHE_VALID / CACHE_REMAP
+  DevBuf<double> cc0, cq0, drift;
   bool eval_pending = false;
   DevBuf<unsigned long long> counters;
   int npairs = 0, nentries = 0;
@@ -123,7 +128,7 @@ struct sh_ctx {
   int64_t neighbor_builds = 0, kernel_launches = 0;
   std::vector<cudaEvent_t> ev, ev2;  // pairs of (start,stop): whole pair phase / evaluation kernel
   size_t ev_used = 0, ev2_used = 0;
-  double sec_pair = 0, sec_neigh = 0, sec_other = 0, sec_run_last = 0, sec_run_total = 0;
+  double sec_pair = 0, sec_neigh = 0, sec_comm = 0, sec_other = 0, sec_run_last = 0, sec_run_total = 0;
   cudaEvent_t run_e0 = nullptr, run_e1 = nullptr;
   int64_t pair_launches = 0;
   // tuning
@@ -220,28 +225,41 @@ int upload_coeffs(sh_ctx *h) {
   return 0;
 }
 
-// exclusive scan of in[0..n) into out[0..n], out[n] = total; returns total through *total_host
-int exclusive_scan(sh_ctx *h, const int *in, int *out, int n, int *total_host) {
+// exclusive scan of in[0..n) into out[0..n], out[n] = total (also left in *d_total on the device)
+int exclusive_scan(sh_ctx *h, const int *in, int *out, int n, int *d_total) {
   const int ntiles = std::max(1, cdiv(n, SCAN_TILE));
   try { h->tile_sum.ensure(ntiles); } catch (std::string &e) { return fail(h, e); }
-  int *d_total = h->scalars.p;
   scan_tile_kernel<<<ntiles, SCAN_THREADS, 0, h->stream>>>(in, out, h->tile_sum.p, n);
   scan_sums_kernel<<<1, 1024, 0, h->stream>>>(h->tile_sum.p, ntiles, d_total);
   scan_add_kernel<<<std::max(1, cdiv(n, 256)), 256, 0, h->stream>>>(out, h->tile_sum.p, n, d_total);
   h->kernel_launches += 3;
-  if (total_host) {
-    CU(cudaMemcpyAsync(h->h_pinned, d_total, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    *total_host = h->h_pinned[0];
-  }
   return 0;
+}
+
+// CUDA-event stopwatch classes on the library stream (rings drained at step boundaries): 0 cull, 1 evaluate, 2 reduce,
+// 3 deep contacts, 4 candidate-cache build, 5 neighbor build, 6 ghost exchange
+int ev_tick(sh_ctx *h, int kind) {
+  if (h->ev2_used + 2 > h->ev2.size()) return 0;
+  h->ev2_kind[h->ev2_used / 2] = kind;
+  if (cudaEventRecord(h->ev2[h->ev2_used], h->stream) != cudaSuccess) return -2;
+  return 0;
+}
+void ev_tock(sh_ctx *h) {
+  if (h->ev2_used + 2 <= h->ev2.size()) { cudaEventRecord(h->ev2[h->ev2_used + 1], h->stream); h->ev2_used += 2; }
 }
 
 int build_neighbors(sh_ctx *h) {
   const int n = (int)h->n, st = h->stride, nown = (int)(h->n - h->nghost);
-  cudaEvent_t e0, e1;
-  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
-  CU(cudaEventRecord(e0, h->stream));
+  if (ev_tick(h, 5)) return -2;
+  // a live candidate cache over the SAME atoms (single rank, no set_atoms in between) survives the rebuild: keep the
+  // old half list so that run_split_pipeline can carry the cache entries over to the new pairs
+  const bool keep_cache = h->cache_state == CACHE_VALID && h->list_valid && h->nghost == 0 && h->npairs > 0 && h->atoms_epoch == h->cache_epoch;
+  if (keep_cache) {
+    try { h->old_half_off.ensure((size_t)nown + 2); h->old_pair_j.ensure((size_t)h->npairs + 1); } catch (std::string &e) { return fail(h, e); }
+    CU(cudaMemcpyAsync(h->old_half_off.p, h->half_off.p, ((size_t)nown + 1) * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->old_pair_j.p, h->pair_j.p, (size_t)h->npairs * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+    h->old_nown = nown;
+  }
   CU(cudaMemsetAsync(h->scalars.p + 1, 0, sizeof(int), h->stream));  // displacement flag
   double rmaxg = 0;
   for (auto &s : h->shapes) rmaxg = std::max(rmaxg, s.rmax);
@@ -298,7 +316,7 @@ int build_neighbors(sh_ctx *h) {
   CU(cudaMemsetAsync(h->cell_count.p, 0, (ncell + 1) * sizeof(int), h->stream));
   CU(cudaMemsetAsync(h->cell_fill.p, 0, (ncell + 1) * sizeof(int), h->stream));
   bin_count_kernel<<<nb, 256, 0, h->stream>>>(h->c.p, n, st, G, h->cell_of.p, h->cell_count.p);
-  if (exclusive_scan(h, h->cell_count.p, h->cell_start.p, (int)ncell, nullptr)) return -1;
+  if (exclusive_scan(h, h->cell_count.p, h->cell_start.p, (int)ncell, h->scalars.p)) return -1;
   bin_fill_kernel<<<nb, 256, 0, h->stream>>>(n, h->cell_of.p, h->cell_start.p, h->cell_fill.p, h->cell_atoms.p);
   bin_sort_kernel<<<cdiv(ncell, 256), 256, 0, h->stream>>>((int)ncell, h->cell_start.p, h->cell_atoms.p);
   const int nbo = std::max(1, cdiv(nown, 256));
@@ -306,8 +324,11 @@ int build_neighbors(sh_ctx *h) {
                                               h->cell_atoms.p, h->cnt_full.p, h->cnt_half.p);
   h->kernel_launches += 4;
   int nentries = 0, npairs = 0;
-  if (exclusive_scan(h, h->cnt_full.p, h->nbr_off.p, nown, &nentries)) return -1;
-  if (exclusive_scan(h, h->cnt_half.p, h->half_off.p, nown, &npairs)) return -1;
+  if (exclusive_scan(h, h->cnt_full.p, h->nbr_off.p, nown, h->scalars.p + 8)) return -1;
+  if (exclusive_scan(h, h->cnt_half.p, h->half_off.p, nown, h->scalars.p + 9)) return -1;
+  CU(cudaMemcpyAsync(h->h_pinned, h->scalars.p + 8, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));   // the one host
+  CU(cudaStreamSynchronize(h->stream));                                                                     // sync of a rebuild
+  nentries = h->h_pinned[0]; npairs = h->h_pinned[1];
   try {
     h->nbr_j.ensure(nentries + 1); h->pair_i.ensure(npairs + 1); h->pair_j.ensure(npairs + 1);
     h->pair_eij.ensure(npairs + 1); h->pair_eji.ensure(npairs + 1); h->pair_img.ensure(npairs + 1);
@@ -321,16 +342,12 @@ int build_neighbors(sh_ctx *h) {
                                                                              h->nbr_j.p, h->pair_eji.p);
   copy_origin_kernel<<<nb, 256, 0, h->stream>>>(h->c.p, h->c0.p, n, st);
   h->kernel_launches += 3;
-  CU(cudaEventRecord(e1, h->stream));
-  CU(cudaEventSynchronize(e1));
-  float ms = 0;
-  cudaEventElapsedTime(&ms, e0, e1);
-  h->sec_neigh += ms * 1e-3;
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  ev_tock(h);
   CU(cudaGetLastError());
   h->npairs = npairs; h->nentries = nentries;
   h->list_valid = true; h->steps_since_build = 0; h->neighbor_builds++;
-  h->cache_valid = false;   // the pair list changed
+  // the pair list changed: a live cache over the same atoms is remapped, anything else is rebuilt
+  h->cache_state = keep_cache ? CACHE_REMAP : CACHE_INVALID;
   return 0;
 }
 
@@ -340,7 +357,7 @@ int drain_events(sh_ctx *h) {
   for (size_t k = 0; k + 1 < h->ev2_used; k += 2) {
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev2[k], h->ev2[k + 1]);
-    double *dst[8] = {&h->sec_cull, &h->sec_eval, &h->sec_reduce, &h->sec_deep, &h->sec_cache, &h->sec_other, &h->sec_other, &h->sec_other};
+    double *dst[8] = {&h->sec_cull, &h->sec_eval, &h->sec_reduce, &h->sec_deep, &h->sec_cache, &h->sec_neigh, &h->sec_comm, &h->sec_other};
     *dst[h->ev2_kind[k / 2] & 7] += ms * 1e-3;
   }
   h->ev2_used = 0;
@@ -430,7 +447,8 @@ int absorb_split_feedback(sh_ctx *h) {
     }
   h->last_records = 0;
   for (int s = 0; s < ns; s++) h->last_records += (long long)std::min<unsigned long long>(sc.pool_count[s], (unsigned long long)h->h_pool_cap[s]);
-  if (*h->h_cache_invalid != 0 && h->cache_valid) { h->cache_valid = false; h->cache_exhausted = true; }
+  // hard flag: that phase already ran on the window path; soft flag: rebuild now, while the cache is still valid
+  if ((h->h_cache_invalid[0] != 0 || h->h_cache_invalid[1] != 0) && h->cache_state != CACHE_INVALID) { h->cache_state = CACHE_INVALID; h->cache_exhausted = true; }
   return 0;
 }
 
@@ -448,45 +466,69 @@ int run_split_pipeline(sh_ctx *h, PairArgs &P) {
   if (!h->h_pool_count) {
     CU(cudaMallocHost(&h->h_pool_count, 8 * sizeof(unsigned long long)));
     CU(cudaMallocHost(&h->h_split_sc, sizeof(SplitScalars)));
-    CU(cudaMallocHost(&h->h_cache_invalid, sizeof(int)));
+    CU(cudaMallocHost(&h->h_cache_invalid, 2 * sizeof(int)));
     CU(cudaEventCreateWithFlags(&h->ev_sc, cudaEventDisableTiming));
   }
   if ((int)h->h_pool_cap.size() != ns) {   // first sizing: 24 records per pair, spread over the shapes, x2
     h->h_pool_cap.assign(ns, std::max<long long>(4096, (long long)np * 24 / std::max(1, ns) * 2));
   }
-  auto tick = [&](int kind) -> int {   // start an event pair of the given class (the rings are drained at step boundaries)
-    if (h->ev2_used + 2 > h->ev2.size()) return 0;
-    h->ev2_kind[h->ev2_used / 2] = kind;
-    if (cudaEventRecord(h->ev2[h->ev2_used], h->stream) != cudaSuccess) return -2;
-    return 0;
-  };
-  auto tock = [&]() { if (h->ev2_used + 2 <= h->ev2.size()) { cudaEventRecord(h->ev2[h->ev2_used + 1], h->stream); h->ev2_used += 2; } };
+  auto tick = [&](int kind) -> int { return ev_tick(h, kind); };
+  auto tock = [&]() { ev_tock(h); };
   const int use_bounds = (h->tune_variant & 2) ? 0 : 1;
   // ---- candidate cache: (re)build when the pair list changed or a particle used up its displacement margin
   CacheArgs C;
   C.enabled = (h->tune_variant & (8 | 2)) ? 0 : 1;   // the cache is built from the direction-cell bounds
   C.invalid = h->scalars.p + 3;
   if (C.enabled) {
-    try { h->cache_hot.ensure((size_t)np + 2); h->cache_count.ensure(2); }
+    const int cur = h->cache_cur;
+    try { h->cache_hot[cur].ensure((size_t)np + 2); h->cache_count.ensure(2); h->fresh_list.ensure((size_t)np + 2); }
     catch (std::string &e) { return fail(h, e); }
-    if (!h->cache_valid) {
+    auto check_validity = [&]() -> int {   // raises the device flag scalars[3] when a particle used up its margin
+      double dmin = 1e300;
+      for (auto &sh : h->shapes) dmin = std::min(dmin, sh.cache_delta[h->cache_level]);
+      CU(cudaMemsetAsync(h->drift.p, 0, 3 * sizeof(double), h->stream));
+      cache_drift_kernel<<<cdiv(h->n, 256), 256, 0, h->stream>>>(view_all(h), h->drift.p);
+      cache_check_kernel<<<cdiv(h->n, 256), 256, 0, h->stream>>>(view_all(h), h->d_shapes.p, h->cache_level, 0.5 * dmin, h->drift.p,
+                                                                 1.0 / (double)h->n, h->scalars.p + 3);
+      h->kernel_launches += 2;
+      return 0;
+    };
+    if (h->cache_state == CACHE_REMAP && h->cache_level + 1 < SH_CACHE_LEVELS && !(h->tune_variant & 32)) {
+      // the pair list was rebuilt over the same atoms: pairs that were in the old list keep their candidates, the new
+      // ones are built with the next larger margin.  No host synchronisation.
+      const int nxt = 1 - cur;
+      try { h->cache_hot[nxt].ensure((size_t)np + 2); h->cache_pool[nxt].ensure((size_t)h->cache_cap + 64); }
+      catch (std::string &e) { return fail(h, e); }
+      if ((rc = check_validity())) return rc;
+      if (tick(4)) return -2;
+      CU(cudaMemsetAsync(h->cache_count.p, 0, 2 * sizeof(unsigned long long), h->stream));
+      CU(cudaMemsetAsync(h->split_flags.p + 2, 0, 2 * sizeof(int), h->stream));
+      C.pool = h->cache_pool[nxt].p; C.hot = h->cache_hot[nxt].p; C.count = h->cache_count.p;
+      C.cap = h->cache_cap; C.overflow = h->split_flags.p + 2; C.level = h->cache_level + 1;
+      cache_remap_kernel<<<cdiv(np, 256), 256, 0, h->stream>>>(P, h->old_half_off.p, h->old_pair_j.p, h->old_nown, h->cache_hot[cur].p,
+                                                                h->cache_pool[cur].p, C, h->fresh_list.p, h->split_flags.p + 3);
+      pair_cache_build_kernel<4><<<std::max(1, std::min(cdiv(np, 4), h->sm_count * 8)), 4 * 32, 0, h->stream>>>(P, C, h->fresh_list.p, h->split_flags.p + 3);
+      tock();
+      h->kernel_launches += 2;
+      h->cache_cur = nxt; h->cache_state = CACHE_VALID; h->cache_remaps++;
+    } else if (h->cache_state != CACHE_VALID) {
       // margin level: a cache that was used up quickly gets a wider margin, one that lived long a tighter one
       if (h->cache_level_pin >= 0) h->cache_level = h->cache_level_pin;
       else if (h->cache_exhausted) {
-        if (h->cache_age < 40 && h->cache_level < SH_CACHE_LEVELS - 1) h->cache_level++;
-        else if (h->cache_age > 600 && h->cache_level > 0) h->cache_level--;
+        if (h->cache_age < 120 && h->cache_level < 2) h->cache_level++;
+        else if (h->cache_age > 1200 && h->cache_level > 0) h->cache_level--;
       }
       h->cache_exhausted = false;
       if (h->cache_cap < (long long)np * 48) h->cache_cap = (long long)np * 48;
       if (tick(4)) return -2;
       for (int attempt = 0;; attempt++) {
         if (attempt > 6) return fail(h, "candidate cache kept overflowing");
-        try { h->cache_pool.ensure((size_t)h->cache_cap + 64); } catch (std::string &e) { return fail(h, e); }
+        try { h->cache_pool[cur].ensure((size_t)h->cache_cap + 64); } catch (std::string &e) { return fail(h, e); }
         CU(cudaMemsetAsync(h->cache_count.p, 0, 2 * sizeof(unsigned long long), h->stream));
         CU(cudaMemsetAsync(h->split_flags.p + 2, 0, sizeof(int), h->stream));
-        C.pool = h->cache_pool.p; C.hot = h->cache_hot.p; C.count = h->cache_count.p;
+        C.pool = h->cache_pool[cur].p; C.hot = h->cache_hot[cur].p; C.count = h->cache_count.p;
         C.cap = h->cache_cap; C.overflow = h->split_flags.p + 2; C.level = h->cache_level;
-        pair_cache_build_kernel<4><<<cdiv(np, 4), 4 * 32, 0, h->stream>>>(P, C);
+        pair_cache_build_kernel<4><<<cdiv(np, 4), 4 * 32, 0, h->stream>>>(P, C, nullptr, nullptr);
         h->kernel_launches++;
         CU(cudaMemcpyAsync(h->h_pool_count, h->cache_count.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
         CU(cudaMemcpyAsync(h->h_pool_count + 1, h->split_flags.p + 2, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -495,19 +537,16 @@ int run_split_pipeline(sh_ctx *h, PairArgs &P) {
         h->cache_cap = (long long)(h->h_pool_count[0] * 3 / 2) + 4096;
       }
       cache_origin_kernel<<<cdiv(h->n, 256), 256, 0, h->stream>>>(view_all(h));
-      CU(cudaMemsetAsync(h->scalars.p + 3, 0, sizeof(int), h->stream));
+      CU(cudaMemsetAsync(h->scalars.p + 3, 0, 2 * sizeof(int), h->stream));
       tock();
       h->kernel_launches++;
-      h->cache_valid = true; h->cache_builds++; h->cache_age = 0;
+      h->cache_state = CACHE_VALID; h->cache_builds++; h->cache_age = 0; h->cache_epoch = h->atoms_epoch;
     } else {
-      double dmin = 1e300;
-      for (auto &sh : h->shapes) dmin = std::min(dmin, sh.cache_delta[h->cache_level]);
-      cache_check_kernel<<<cdiv(h->n, 256), 256, 0, h->stream>>>(view_all(h), h->d_shapes.p, h->cache_level, 0.5 * dmin, h->scalars.p + 3);
-      h->kernel_launches++;
+      if ((rc = check_validity())) return rc;
     }
     h->cache_age++;
   }
-  C.pool = h->cache_pool.p; C.hot = h->cache_hot.p; C.count = h->cache_count.p;
+  C.pool = h->cache_pool[h->cache_cur].p; C.hot = h->cache_hot[h->cache_cur].p; C.count = h->cache_count.p;
   C.cap = h->cache_cap; C.overflow = h->split_flags.p + 2; C.level = h->cache_level;
   std::vector<long long> base(ns);
   long long tot = 0;
@@ -564,7 +603,7 @@ int run_split_pipeline(sh_ctx *h, PairArgs &P) {
     h->kernel_launches++;
   }
   CU(cudaMemcpyAsync(h->h_split_sc, h->split_sc.p, sizeof(SplitScalars), cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaMemcpyAsync(h->h_cache_invalid, h->scalars.p + 3, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(h->h_cache_invalid, h->scalars.p + 3, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaEventRecord(h->ev_sc, h->stream));
   h->sc_pending = true; h->sc_nshape = ns;
   return 0;
@@ -668,7 +707,7 @@ int sh_create(sh_ctx **out, int device_id) {
   h->pk.assign(SH_MAX_SHAPES * SH_MAX_SHAPES, 1.0);
   h->pm.assign(SH_MAX_SHAPES * SH_MAX_SHAPES, 1.0);
   try {
-    h->scalars.ensure(16); h->bbox.ensure(8); h->counters.ensure(16);
+    h->scalars.ensure(16); h->bbox.ensure(8); h->counters.ensure(16); h->drift.ensure(4);
   } catch (std::string &) { delete h; return -7; }
   cudaMemset(h->scalars.p, 0, 16 * sizeof(int));
   cudaMemset(h->counters.p, 0, 16 * sizeof(unsigned long long));
@@ -696,8 +735,9 @@ int sh_destroy(sh_ctx *h) {
   for (auto &e : h->ev) cudaEventDestroy(e);
   for (auto &e : h->ev2) cudaEventDestroy(e);
   h->pool.release(); h->pool_flag.release(); h->pool_base.release(); h->pool_cap.release(); h->split_sc.release(); h->eval_plan.release(); h->slow_list.release();
-  h->pd.release(); h->cache_hot.release(); h->big_list.release(); h->split_flags.release();
-  h->cache_pool.release(); h->cache_count.release(); h->cc0.release(); h->cq0.release();
+  h->pd.release(); h->big_list.release(); h->split_flags.release();
+  for (int k = 0; k < 2; k++) { h->cache_hot[k].release(); h->cache_pool[k].release(); }
+  h->old_half_off.release(); h->old_pair_j.release(); h->fresh_list.release(); h->cache_count.release(); h->cc0.release(); h->cq0.release(); h->drift.release();
   if (h->h_pool_count) { cudaFreeHost(h->h_pool_count); cudaFreeHost(h->h_split_sc); cudaFreeHost(h->h_cache_invalid); cudaEventDestroy(h->ev_sc); }
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   h->stage.release();
@@ -799,6 +839,7 @@ int sh_set_atoms(sh_ctx *h, int64_t n, const int64_t *tag, const int *shape, con
   h->tag.resize(n);
   for (int64_t i = 0; i < n; i++) h->tag[i] = tag ? tag[i] : i + 1;
   h->forces_valid = false; h->list_valid = false; h->npairs = 0; h->nentries = 0; h->nghost = 0;
+  h->atoms_epoch++; h->cache_state = CACHE_INVALID;
   return 0;
 }
 
@@ -845,7 +886,7 @@ int sh_set_pair_tuning(sh_ctx *h, int threads_per_cta, int ctas_per_sm, int vari
   if (threads_per_cta != 0 && threads_per_cta != 64 && threads_per_cta != 128 && threads_per_cta != 256 && threads_per_cta != 384 && threads_per_cta != 512)
     return fail(h, "threads_per_cta must be 0, 64, 128, 256 or 512");
   h->tune_threads = threads_per_cta; h->tune_ctas_per_sm = ctas_per_sm; h->tune_variant = variant;
-  h->cache_valid = false;
+  h->cache_state = CACHE_INVALID;
   return 0;
 }
 
@@ -1233,14 +1274,15 @@ int sh_reset_timers(sh_ctx *h) {
   CU(cudaSetDevice(h->device));
   int rc = drain_events(h);
   if (rc) return rc;
-  h->sec_pair = h->sec_neigh = h->sec_other = 0; h->pair_launches = 0; h->sec_run_total = 0;
-  h->sec_eval = h->sec_cull = h->sec_reduce = h->sec_deep = 0; h->eval_launches = 0; h->big_pairs = 0; h->slow_pairs = 0; h->pool_grows = 0; h->cache_builds = 0; h->sec_cache = 0;
+  h->sec_pair = h->sec_neigh = h->sec_comm = h->sec_other = 0; h->pair_launches = 0; h->sec_run_total = 0;
+  h->sec_eval = h->sec_cull = h->sec_reduce = h->sec_deep = 0; h->eval_launches = 0; h->big_pairs = 0; h->slow_pairs = 0; h->pool_grows = 0; h->cache_builds = 0; h->cache_remaps = 0; h->sec_cache = 0;
   h->neighbor_builds = 0; h->kernel_launches = 0;
   CU(cudaMemset(h->counters.p, 0, 16 * sizeof(unsigned long long)));
   return 0;
 }
 
-int sh_get_cache_stats(const sh_ctx *hc, int64_t *cache_builds, double *seconds_cache, int *level, int64_t *slow_pairs) {
+int sh_get_cache_stats(const sh_ctx *hc, int64_t *cache_builds, double *seconds_cache, int *level, int64_t *slow_pairs,
+                       int64_t *cache_remaps) {
   sh_ctx *h = const_cast<sh_ctx *>(hc);
   CU(cudaSetDevice(h->device));
   int rc = drain_events(h);
@@ -1250,6 +1292,7 @@ int sh_get_cache_stats(const sh_ctx *hc, int64_t *cache_builds, double *seconds_
   if (seconds_cache) *seconds_cache = h->sec_cache;
   if (level) *level = h->cache_level;
   if (slow_pairs) *slow_pairs = h->slow_pairs;
+  if (cache_remaps) *cache_remaps = h->cache_remaps;
   return 0;
 }
 
@@ -1262,7 +1305,7 @@ int sh_set_tuning(sh_ctx *h, const char *key, double value) {
   else if (k == "eval_pts") { if (v != 0 && v != 2 && v != 4) return fail(h, "eval_pts must be 0, 2 or 4"); h->eval_pts = v; }
   else if (k == "eval_occ") { if (v != 0 && v != 3 && v != 4) return fail(h, "eval_occ must be 0, 3 or 4"); h->eval_occ = v; }
   else if (k == "eval_mode") { if (v < 0 || v > 2) return fail(h, "eval_mode must be 0 (default), 1 (one block per CTA) or 2 (persistent chunks)"); h->eval_mode = v; }
-  else if (k == "cache_level") { if (v < -1 || v >= SH_CACHE_LEVELS) return fail(h, "cache_level must be -1 (adaptive) .. 2"); h->cache_level_pin = v; h->cache_valid = false; }
+  else if (k == "cache_level") { if (v < -1 || v >= SH_CACHE_LEVELS) return fail(h, "cache_level must be -1 (adaptive) .. 2"); if (v > 2) return fail(h, "cache_level must be -1 (adaptive) .. 2"); h->cache_level_pin = v; h->cache_state = CACHE_INVALID; }
   else if (k == "cube_n") {
     if (!h->shapes.empty()) return fail(h, "cube_n must be set before add_shape");
     if (v != 0 && (v < 8 || v > 144)) return fail(h, "cube_n must be 0 (default) or 8..144");

@@ -83,16 +83,28 @@ __global__ void unpack_atoms_kernel(AtomView A, int first, int m, const double *
   for (int d = 0; d < 4; d++) A.q[d * st + i] = in[7 * (size_t)k + 3 + d];
 }
 
-// candidate cache (pair_split_kernels.cuh): a node of atom i has moved, relative to any partner frame, by at most
-// w_i = |c - c0| + angle(q0 -> q) * (rmax_i + delta_i); the cache stays valid while every w_i <= thresh.
-__global__ void cache_check_kernel(AtomView A, const DevShape *shapes, int level, double thresh, int *flag) {
+// candidate cache (pair_split_kernels.cuh): what matters is how far a node of atom a has moved RELATIVE to its partner b.
+// For any common vector u:  |dc_a - dc_b| <= |dc_a - u| + |dc_b - u|, so with u = the mean displacement of all atoms
+// since the cache was built (a bulk flow moves every atom but no pair) a node of atom i has moved, relative to any
+// partner frame, by at most  w_i = |dc_i - u| + angle(q0 -> q) * (rmax_i + delta_i); the cache stays valid while every
+// w_i <= thresh.  u only steers WHEN the cache is rebuilt, never a force: its (atomic, order-dependent) sum is harmless.
+__global__ void cache_drift_kernel(AtomView A, double *acc /* 3: sum of c - cc0 */) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int st = A.stride;
+  double d0 = 0, d1 = 0, d2 = 0;
+  if (i < A.n) { d0 = A.c[i] - A.cc0[i]; d1 = A.c[st + i] - A.cc0[st + i]; d2 = A.c[2 * st + i] - A.cc0[2 * st + i]; }
+  d0 = warp_sum(d0); d1 = warp_sum(d1); d2 = warp_sum(d2);
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&acc[0], d0); atomicAdd(&acc[1], d1); atomicAdd(&acc[2], d2); }
+}
+__global__ void cache_check_kernel(AtomView A, const DevShape *shapes, int level, double thresh, const double *acc, double inv_n,
+                                   int *flag) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= A.n) return;
   const int st = A.stride;
   const DevShape &s = shapes[A.shape[i]];
   double u2 = 0, dm = 0, dp = 0;
 #pragma unroll
-  for (int d = 0; d < 3; d++) { const double dd = A.c[d * st + i] - A.cc0[d * st + i]; u2 += dd * dd; }
+  for (int d = 0; d < 3; d++) { const double dd = (A.c[d * st + i] - A.cc0[d * st + i]) - acc[d] * inv_n; u2 += dd * dd; }
 #pragma unroll
   for (int d = 0; d < 4; d++) {
     const double a = A.q[d * st + i], b = A.cq0[d * st + i];
@@ -101,7 +113,8 @@ __global__ void cache_check_kernel(AtomView A, const DevShape *shapes, int level
   const double dq = sqrt(fmin(dm, dp));                 // = 2 sin(angle/4)
   const double ang = dq < 0.2 ? 2.02 * dq : 10.0;       // angle <= 2.02 dq for small rotations
   const double w = sqrt(u2) + ang * (s.rmax + s.cache_delta[level]);
-  if (!(w <= thresh)) *flag = 1;
+  if (!(w <= thresh)) flag[0] = 1;            // margin used up: the cached cull stands down this step
+  else if (!(w <= 0.75 * thresh)) flag[1] = 1;  // nearly used up: the host rebuilds the cache before the next phase
 }
 __global__ void cache_origin_kernel(AtomView A) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

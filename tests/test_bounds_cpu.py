@@ -95,12 +95,12 @@ def test_direction_cell_tables_are_proven_bounds(harness, name, lmax, make, cn_r
     t = harness.sth_build(lmax, a.ctypes.data, b.ctypes.data, 1.0, nt, nphi, cn_req, err, 256)
     assert t, err.value
     cn = harness.sth_cube_n(t)
-    sc = np.zeros(12)
+    sc = np.zeros(13)
     harness.sth_scalars(t, sc.ctypes.data)
     rmax, rmin, h1, h2, step, pad, r_sup, r_inf = sc[0], sc[1], sc[3], sc[4], sc[5], sc[6], sc[7], sc[8]
-    deltas = sc[9:12]
+    deltas = sc[9:13]
     nc = 6 * cn * cn
-    ub2, lb2, wide2 = np.zeros(nc, np.float32), np.zeros(nc, np.float32), np.zeros(3 * nc, np.float32)
+    ub2, lb2, wide2 = np.zeros(nc, np.float32), np.zeros(nc, np.float32), np.zeros(4 * nc, np.float32)
     harness.sth_cube(t, ub2.ctypes.data, lb2.ctypes.data, wide2.ctypes.data)
     o = O.Oracle()
     o.set_quadrature(nt, nphi)
@@ -165,7 +165,7 @@ def test_direction_cell_tables_are_proven_bounds(harness, name, lmax, make, cn_r
     shell = np.sqrt(ub2[cell].astype(np.float64)) - np.sqrt(lb2[cell].astype(np.float64))
     assert np.median(shell) < 0.06 * rmax, np.median(shell)     # and not uselessly loose
     # candidate-cache tables: a node cached at direction d0 may drift by <= gamma before the cache is rebuilt
-    for lv in range(3):
+    for lv in range(4):
         delta = deltas[lv]
         gamma = np.arcsin(min(1.0, delta / (rmin + 2 * delta)))
         d0 = d[:60000]

@@ -239,14 +239,18 @@ def test_candidate_cache_matches_window_path_over_a_run():
     rng = np.random.default_rng(3)
     cfg["angmom"] = rng.normal(0, 2.0, size=cfg["x"].shape)       # fast spins: rotation must trigger rebuilds too
     res = []
-    for variant in (16, 24):
+    for variant in (16, 24, 48):     # cache with remap across neighbor rebuilds / cache off / cache without remap
         g = pkg.ShGpu(); W.apply(g, cfg); g.set_pair_tuning(0, 0, variant)
         g.compute_forces(); g.reset_timers(); g.run(400)
-        res.append((g.get_atoms(), g.get_counters(), g.get_split_stats())); g.close()
-    (a0, c0, s0), (a1, c1, s1) = res
+        res.append((g.get_atoms(), g.get_counters(), dict(g.get_split_stats(), **g.get_cache_stats()))); g.close()
+    (a0, c0, s0), (a1, c1, s1), (a2, c2, s2) = res
+    assert s0["cache_remaps"] >= 3 and s2["cache_remaps"] == 0, (s0, s2)
+    assert c2["nodes_inside"] == c1["nodes_inside"]
+    for k in ("x", "v", "quat", "angmom"):
+        assert np.abs(a2[k] - a1[k]).max() <= 1e-9 * max(1.0, np.abs(a1[k]).max()), k
     assert c0["nodes_inside"] == c1["nodes_inside"] and c0["pair_evals"] == c1["pair_evals"]
     assert c0["nodes_inside"] > 1000
-    builds = s0["cache_builds"]
+    builds = s0["cache_builds"] + s0["cache_remaps"]
     assert builds >= 3, "cache was rebuilt %d times; the test must exercise the displacement trigger" % builds
     assert c0["nodes_transformed"] < 0.5 * c1["nodes_transformed"]
     for k in ("x", "v", "quat", "angmom"):
