@@ -79,6 +79,26 @@ int sh_set_ghost_count(sh_ctx *h, int64_t nghost);
 int sh_pack_atoms(sh_ctx *h, int64_t m, const int *d_idx, const double *d_shift, double *d_out);
 int sh_unpack_ghosts(sh_ctx *h, int64_t first, int64_t m, const double *d_in);
 
+/* Multi-GPU behind the C ABI (replaces Comm::exchange / Comm::borders / forward_comm of LAMMPS' CommBrick
+ * for this atom style).  One handle = one rank = one GPU; ranks are processes (torchrun / MPI) or threads of one process.
+ * Rank 0 calls sh_dd_unique_id (an ncclUniqueId, 128 bytes) and the host distributes it (MPI_Bcast, torch.distributed, a
+ * shared variable between threads); every rank then calls sh_dd_init BEFORE sh_set_atoms.  From then on sh_set_box takes
+ * the GLOBAL box, sh_set_atoms may be handed all atoms on every rank (each keeps the ones inside its brick), and sh_run /
+ * sh_compute_forces are collective: ghost exchange every step, atom migration + border lists on neighbor-rebuild steps,
+ * all on the device with NCCL point-to-point inside the library.  pgrid = NULL (or zeros) picks the brick grid.
+ * Read-back calls see this rank's atoms: owned first, then ghosts (sh_dd_get_info, sh_get_tags). */
+int sh_dd_unique_id(char *id, int cap);
+int sh_dd_init(sh_ctx *h, int rank, int nranks, const char *id, const int *pgrid);
+int sh_dd_get_info(const sh_ctx *h, int pgrid[3], int brick[3], int64_t *nlocal, int64_t *nghost,
+                   int64_t *migrated, int64_t *border_builds);
+int sh_get_tags(const sh_ctx *h, int64_t n, int64_t *tags);
+/* per-step device times (ms) of the last sh_run when the "step_trace" knob is on (at most 4096 steps); flags: bit 0 the
+ * step rebuilt the neighbor list, bit 1 rebuilt the candidate cache, bit 2 remapped it */
+int sh_get_step_trace(const sh_ctx *h, int64_t cap, int64_t *nsteps, double *ms, int *flags);
+/* fix deform xy + remap v (Lees-Edwards shear, BASELINE configs[3]): flow along x, gradient along y, rate = dvx/dy.
+ * Before sh_set_atoms; needs a box periodic in x and y; x is never decomposed. */
+int sh_set_shear(sh_ctx *h, double rate);
+
 /* Pair::compute-style offload for a host code that owns the atoms (the drop-in a LAMMPS pair style
  * wrapper uses every step): push x / quat (v, angmom optional; NULL = keep), sh_compute_forces,
  * then read f / torque.  The neighbor list is kept across calls and rebuilt when the skin is
@@ -133,7 +153,12 @@ int sh_set_pair_tuning(sh_ctx *h, int threads_per_cta, int ctas_per_sm, int vari
  * lanes per pair in that kernel (16, 32; default 16); "eval_pts" points per lane of pair_eval_kernel (2, 4; default 4);
  * "eval_occ" its minimum CTAs per SM at 2 points (3, 4); "eval_mode" 1 = one block per CTA (default), 2 = persistent
  * chunks; "cache_level" margin level of the candidate cache (-1 adaptive (default), 0..2 = 0.5 / 1 / 2 % of rmax);
- * "cube_n" direction cells per cube-face edge of the per-shape bound tables (8..144, default 144; before sh_add_shape) */
+ * "cube_n" direction cells per cube-face edge of the per-shape bound tables (8..144, default 144; before sh_add_shape);
+ * "sync_rebuild" 1 = sh_run decides neighbor rebuilds from the current step's displacement flag (one host round trip per
+ * step) instead of the one-step-ahead prediction (default 0: the host never waits for the device inside sh_run);
+ * "step_trace" 1 = record a CUDA event per step in sh_run (sh_get_step_trace);
+ * "dd_self_ghosts" 1 = (testing) with the decomposition on, periodic dimensions are served by ghost images even when they
+ * are not divided, so that one GPU exercises migration, border lists and the ghost exchange against itself */
 int sh_set_tuning(sh_ctx *h, const char *key, double value);
 
 /* FP64 FMA-pipe peak microbenchmark (K0): returns measured DFMA flop/s of the device ----------- */

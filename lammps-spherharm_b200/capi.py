@@ -62,6 +62,7 @@ class ShGpu:
             self.h = None
             raise ShGpuError("sh_create failed (rc=%d): no usable CUDA device; libshgpu has no CPU fallback" % rc)
         self.n = 0
+        self.dd = False
 
     def close(self):
         if getattr(self, "h", None):
@@ -115,7 +116,7 @@ class ShGpu:
         tag = None if tag is None else np.ascontiguousarray(tag, dtype=np.int64)
         self._ck(self.L.sh_set_atoms(self.h, C.c_int64(n), _p(tag, c_lp), _p(shape, c_ip), _p(x), _p(v), _p(quat),
                                      _p(angmom)))
-        self.n = n
+        self.n = self.refresh_n() if self.dd else n
 
     def pair_coeff(self, si, sj, k, exponent):
         self._ck(self.L.sh_pair_coeff(self.h, int(si), int(sj), C.c_double(k), C.c_double(exponent)))
@@ -162,6 +163,52 @@ class ShGpu:
         def ptr(a):
             return C.cast(a, c_dp) if isinstance(a, int) else a.ctypes.data_as(c_dp)
         self._ck(self.L.sh_get_forces(self.h, C.c_int64(self.n), ptr(f), ptr(torque)))
+
+    # ---- in-library domain decomposition (NCCL inside libshgpu) -------------------------------------
+    @staticmethod
+    def dd_unique_id():
+        L = load_library()
+        buf = C.create_string_buffer(128)
+        rc = L.sh_dd_unique_id(buf, 128)
+        if rc != 0:
+            raise ShGpuError("sh_dd_unique_id failed (rc=%d): NCCL not available" % rc)
+        return buf.raw
+
+    def dd_init(self, rank, nranks, uid=None, pgrid=None):
+        pg = None if pgrid is None else np.ascontiguousarray(pgrid, dtype=np.int32)
+        self._ck(self.L.sh_dd_init(self.h, int(rank), int(nranks), uid, _p(pg, c_ip)))
+        self.dd = True
+
+    def dd_info(self):
+        pg, br = np.zeros(3, np.int32), np.zeros(3, np.int32)
+        v = [C.c_int64() for _ in range(4)]
+        self._ck(self.L.sh_dd_get_info(self.h, _p(pg, c_ip), _p(br, c_ip), *[C.byref(t) for t in v]))
+        return dict(pgrid=tuple(int(a) for a in pg), brick=tuple(int(a) for a in br), nlocal=v[0].value, nghost=v[1].value,
+                    migrated=v[2].value, border_builds=v[3].value)
+
+    def get_tags(self):
+        self.refresh_n()
+        t = np.zeros(self.n, dtype=np.int64)
+        self._ck(self.L.sh_get_tags(self.h, C.c_int64(self.n), _p(t, c_lp)))
+        return t
+
+    def get_step_trace(self):
+        n = C.c_int64(0)
+        self._ck(self.L.sh_get_step_trace(self.h, C.c_int64(0), C.byref(n), None, None))
+        ms, fl = np.zeros(n.value), np.zeros(n.value, dtype=np.int32)
+        self._ck(self.L.sh_get_step_trace(self.h, C.c_int64(n.value), C.byref(n), _p(ms), _p(fl, c_ip)))
+        return ms, fl
+
+    def set_shear(self, rate):
+        self._ck(self.L.sh_set_shear(self.h, C.c_double(rate)))
+        self.dd = True
+
+    def refresh_n(self):
+        """owned + ghost atoms of this rank (changes when the decomposition migrates atoms)"""
+        n = C.c_int64(0)
+        self.L.sh_get_natoms(self.h, C.byref(n))
+        self.n = n.value
+        return self.n
 
     # ---- multi-rank support (decomp.py drives these) ------------------------------------------
     def set_ghost_count(self, nghost):
@@ -211,7 +258,7 @@ class ShGpu:
 
     # ---- read-back ---------------------------------------------------------------------------
     def get_atoms(self, fields=("x", "v", "quat", "angmom", "f", "torque")):
-        n = self.n
+        n = self.refresh_n() if self.dd else self.n
         shapes = dict(x=3, v=3, quat=4, angmom=3, f=3, torque=3)
         out = {k: (np.zeros((n, shapes[k])) if k in fields else None) for k in shapes}
         self._ck(self.L.sh_get_atoms(self.h, C.c_int64(n), _p(out["x"]), _p(out["v"]), _p(out["quat"]),

@@ -1,0 +1,51 @@
+// dd_types.h — state of the in-library domain decomposition (see dd_host.cuh)
+#pragma once
+#include <nccl.h>
+
+#include <string>
+#include <vector>
+
+#include "decomp_kernels.cuh"
+
+namespace shgpu {
+
+struct NcclApi {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  std::string err;
+};
+
+
+struct DdCtx {
+  bool on = false, geometry_ok = false, borders_ok = false, pgrid_set = false;
+  int rank = 0, nranks = 1;
+  NcclApi *nccl = nullptr;
+  ncclComm_t comm = nullptr;
+  int pgrid[3] = {1, 1, 1}, g[3] = {0, 0, 0};
+  double glo[3] = {0, 0, 0}, ghi[3] = {0, 0, 0}, glen[3] = {0, 0, 0};
+  int gper[3] = {0, 0, 0};
+  DdGeom G{};
+  std::vector<int> nbr_rank, slot_lo, slot_hi;   // distinct neighbour ranks (ascending) and their slot ranges
+  std::vector<int> mig_rank;                     // the same without this rank (migration targets)
+  std::vector<int> send_cnt, recv_cnt;           // ghosts per neighbour rank of the forward exchange
+  std::vector<double> base_shift;                // periodic shift per slot (without the Lees-Edwards offset)
+  int nsend = 0, ghost_vel = 0;
+  bool self_ghosts = false;                      // test knob: periodic dims get ghost images even when undivided
+  double le_rate = 0, le_off_build = 0, le_time_build = 0;   // Lees-Edwards: shear rate, image offset at the last rebuild
+  DevBuf<int> flag, pos, order, d_int, send_idx, send_slot, shape2;
+  DevBuf<double> sendbuf, recvbuf, x2, v2, q2, L2;
+  DevBuf<long long> tag2;
+  int stride2 = 0;
+  int *h_int = nullptr;                          // pinned, 256 ints
+  int64_t migrated_out = 0, migrated_in = 0, border_builds = 0;
+};
+
+}  // namespace shgpu

@@ -1,0 +1,192 @@
+// decomp_kernels.cuh — device side of the spatial domain decomposition (row a12).
+// Replaces the Comm::exchange / Comm::borders / forward_comm path of upstream LAMMPS' CommBrick (reference source NOT
+// IN MOUNT) for the SPHERHARM atom style: everything that touches per-atom data runs on the device; the host only sees
+// a handful of counters per neighbor rebuild.  Lees-Edwards shear (BASELINE configs[3], "periodic shear box"): flow
+// along x, gradient along y; an atom (or ghost image) that crosses the y boundary n times is displaced by -n * le_offset
+// along x and its velocity by -n * le_vshear (fix deform xy + remap v in LAMMPS terms).
+#pragma once
+#include "step_kernels.cuh"
+
+namespace shgpu {
+
+constexpr int DD_MAX_RANKS = 64;
+
+struct DdGeom {
+  double glo[3], L[3], mylo[3], myhi[3], sub[3], rc;
+  int gper[3], pgrid[3], ghosted[3];
+  int nslot;                 // active neighbour offsets, sorted by (destination rank, offset id)
+  int off[26][3];
+  double shift[26][3];       // added to x of an atom sent through this slot (periodic image; includes the current
+                             // Lees-Edwards offset for slots that cross y)
+  double vshift[26];         // added to v_x of such an image
+  double le_offset, le_vshear;   // current image offset along x per +1 crossing of y, and its rate * L_y
+  signed char key_of_rank[DD_MAX_RANKS];   // migration key of a destination rank: 0 = stays, 1 + k = k-th distinct
+                                           // neighbour rank, -1 = not a neighbour (lost atom)
+};
+
+// wrap owned positions into the global box (periodic dims), find the owning brick of every owned atom and raise its
+// key flag: flag[key * n + i] = 1 (the matrix is zeroed by the caller)
+__global__ void dd_wrap_owner_kernel(AtomView A, DdGeom G, int *flag, int *lost) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n) return;
+  const int st = A.stride;
+  double x[3] = {A.x[i], A.x[st + i], A.x[2 * st + i]};
+  if (G.gper[1]) {   // y first: a crossing shifts x (Lees-Edwards), then x wraps
+    const double ny = floor((x[1] - G.glo[1]) / G.L[1]);
+    if (ny != 0.0) {
+      x[1] -= G.L[1] * ny;
+      if (G.le_offset != 0.0 || G.le_vshear != 0.0) { x[0] -= ny * G.le_offset; A.v[i] -= ny * G.le_vshear; }
+    }
+  }
+  if (G.gper[0]) x[0] -= G.L[0] * floor((x[0] - G.glo[0]) / G.L[0]);
+  if (G.gper[2]) x[2] -= G.L[2] * floor((x[2] - G.glo[2]) / G.L[2]);
+  int gi[3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    A.x[d * st + i] = x[d];
+    const int c = (int)floor((x[d] - G.glo[d]) / G.sub[d]);
+    gi[d] = min(max(c, 0), G.pgrid[d] - 1);
+  }
+  const int r = (gi[0] * G.pgrid[1] + gi[1]) * G.pgrid[2] + gi[2];
+  int key = G.key_of_rank[r];
+  if (key < 0) { atomicAdd(lost, 1); key = 0; }
+  flag[(size_t)key * A.n + i] = 1;
+}
+
+// after the exclusive scan `pos` of a (nkey x n) flag matrix: start of every key block, and the stable order list
+__global__ void dd_starts_kernel(const int *pos, int nkey, int n, int *starts /* nkey + 1 */) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k <= nkey) starts[k] = pos[(size_t)k * n];
+}
+__global__ void dd_order_kernel(size_t total, int n, const int *flag, const int *pos, int *order, int *order_key) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  if (flag[t]) { const int p = pos[t]; order[p] = (int)(t % n); if (order_key) order_key[p] = (int)(t / n); }
+}
+// counts per destination rank from the key / slot starts: cnt[k] = starts[hi[k]] - starts[lo[k]]
+__global__ void dd_counts_kernel(const int *starts, int ngroups, const int *lo, const int *hi, int *cnt) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < ngroups) cnt[k] = starts[hi[k]] - starts[lo[k]];
+}
+
+// migration record: tag, shape, x3, v3, quat4, angmom3 = 15 doubles (+1 pad)
+#define DD_MIGREC 16
+__global__ void dd_pack_migrants_kernel(AtomView A, const long long *tag, int m, const int *list, double *out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m) return;
+  const int i = list[k], st = A.stride;
+  double *o = out + (size_t)DD_MIGREC * k;
+  o[0] = (double)tag[i]; o[1] = (double)A.shape[i]; o[2] = 0.0;
+#pragma unroll
+  for (int d = 0; d < 3; d++) { o[3 + d] = A.x[d * st + i]; o[6 + d] = A.v[d * st + i]; o[13 + d] = A.L[d * st + i]; }
+#pragma unroll
+  for (int d = 0; d < 4; d++) o[9 + d] = A.q[d * st + i];
+}
+
+// new owned arrays: stayers (old order) followed by the arrivals (source rank order)
+struct OwnedArrays { double *x, *v, *q, *L; int *shape; long long *tag; int stride; };
+__global__ void dd_compact_kernel(OwnedArrays src, OwnedArrays dst, int nstay, const int *stay_list, int narr, const double *arr) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < nstay) {
+    const int i = stay_list[k];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      dst.x[d * dst.stride + k] = src.x[d * src.stride + i];
+      dst.v[d * dst.stride + k] = src.v[d * src.stride + i];
+      dst.L[d * dst.stride + k] = src.L[d * src.stride + i];
+    }
+#pragma unroll
+    for (int d = 0; d < 4; d++) dst.q[d * dst.stride + k] = src.q[d * src.stride + i];
+    dst.shape[k] = src.shape[i]; dst.tag[k] = src.tag[i];
+  } else if (k < nstay + narr) {
+    const double *o = arr + (size_t)DD_MIGREC * (k - nstay);
+#pragma unroll
+    for (int d = 0; d < 3; d++) { dst.x[d * dst.stride + k] = o[3 + d]; dst.v[d * dst.stride + k] = o[6 + d]; dst.L[d * dst.stride + k] = o[13 + d]; }
+#pragma unroll
+    for (int d = 0; d < 4; d++) dst.q[d * dst.stride + k] = o[9 + d];
+    dst.shape[k] = (int)o[1]; dst.tag[k] = (long long)o[0];
+  }
+}
+// same arrays, new stride (capacity growth that keeps the first n atoms)
+__global__ void dd_restride_kernel(OwnedArrays src, OwnedArrays dst, int n) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    dst.x[d * dst.stride + k] = src.x[d * src.stride + k];
+    dst.v[d * dst.stride + k] = src.v[d * src.stride + k];
+    dst.L[d * dst.stride + k] = src.L[d * src.stride + k];
+  }
+#pragma unroll
+  for (int d = 0; d < 4; d++) dst.q[d * dst.stride + k] = src.q[d * src.stride + k];
+  dst.shape[k] = src.shape[k]; dst.tag[k] = src.tag[k];
+}
+
+// border flags: flag[s * nown + i] = owned atom i lies in the shell that neighbour slot s needs as ghosts
+__global__ void dd_border_flag_kernel(AtomView A, DdGeom G, int *flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n) return;
+  const int st = A.stride;
+  int hi[3], lo[3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    const double x = A.x[d * st + i];
+    hi[d] = G.ghosted[d] && x >= G.myhi[d] - G.rc;
+    lo[d] = G.ghosted[d] && x < G.mylo[d] + G.rc;
+  }
+  for (int s = 0; s < G.nslot; s++) {
+    bool in = true;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      if (G.off[s][d] == 1) in = in && hi[d];
+      else if (G.off[s][d] == -1) in = in && lo[d];
+    }
+    flag[(size_t)s * A.n + i] = in ? 1 : 0;
+  }
+}
+
+// ghost records.  border records (full = 1): tag, shape, then the per-step part; per-step part: x + shift, quat
+// [, v + vshift, angmom when with_vel]
+__global__ void dd_pack_kernel(AtomView A, const long long *tag, DdGeom G, int m, const int *send_idx, const int *send_slot,
+                               int full, int with_vel, double *out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m) return;
+  const int i = send_idx[k], s = send_slot[k], st = A.stride;
+  const int w = (full ? 2 : 0) + 7 + (with_vel ? 6 : 0);
+  double *o = out + (size_t)w * k;
+  int b = 0;
+  if (full) { o[0] = (double)tag[i]; o[1] = (double)A.shape[i]; b = 2; }
+#pragma unroll
+  for (int d = 0; d < 3; d++) o[b + d] = A.x[d * st + i] + G.shift[s][d];
+#pragma unroll
+  for (int d = 0; d < 4; d++) o[b + 3 + d] = A.q[d * st + i];
+  if (with_vel) {
+#pragma unroll
+    for (int d = 0; d < 3; d++) { o[b + 7 + d] = A.v[d * st + i] + (d == 0 ? G.vshift[s] : 0.0); o[b + 10 + d] = A.L[d * st + i]; }
+  }
+}
+__global__ void dd_unpack_kernel(AtomView A, long long *tag, int first, int m, int full, int with_vel, const double *in) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m) return;
+  const int i = first + k, st = A.stride;
+  const int w = (full ? 2 : 0) + 7 + (with_vel ? 6 : 0);
+  const double *o = in + (size_t)w * k;
+  int b = 0;
+  if (full) {
+    tag[i] = (long long)o[0]; A.shape[i] = (int)o[1]; b = 2;
+    if (!with_vel) {
+#pragma unroll
+      for (int d = 0; d < 3; d++) { A.v[d * st + i] = 0.0; A.L[d * st + i] = 0.0; }
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; d++) A.x[d * st + i] = o[b + d];
+#pragma unroll
+  for (int d = 0; d < 4; d++) A.q[d * st + i] = o[b + 3 + d];
+  if (with_vel) {
+#pragma unroll
+    for (int d = 0; d < 3; d++) { A.v[d * st + i] = o[b + 7 + d]; A.L[d * st + i] = o[b + 10 + d]; }
+  }
+}
+
+}  // namespace shgpu

@@ -14,6 +14,8 @@
 #include <vector>
 
 #include "../../include/shgpu.h"
+#include "devbuf.h"
+#include "dd_types.h"
 #include "neighbor_kernels.cuh"
 #include "pair_kernel.cuh"
 #include "pair_warp_kernel.cuh"
@@ -24,20 +26,6 @@
 using namespace shgpu;
 
 namespace {
-
-template <class T>
-struct DevBuf {
-  T *p = nullptr;
-  size_t cap = 0;
-  void ensure(size_t n) {
-    if (n <= cap) return;
-    if (p) cudaFree(p);
-    size_t want = std::max<size_t>(n, cap + cap / 2);
-    if (cudaMalloc(&p, want * sizeof(T)) != cudaSuccess) { p = nullptr; cap = 0; throw std::string("cudaMalloc failed"); }
-    cap = want;
-  }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
 
 struct ShapeDev {
   DevBuf<double> Ap, node;   // node: 6 x nq
@@ -78,7 +66,21 @@ struct sh_ctx {
   int stride = 0;
   DevBuf<double> x, v, q, L, f, tq, c, Rs, c0, wallf, ewall, ke;
   DevBuf<int> shape;
-  std::vector<int64_t> tag;
+  std::vector<int64_t> tag;          // host mirror of d_tag (owned + ghost order); refreshed lazily
+  DevBuf<long long> d_tag;
+  bool tags_host_valid = true;
+  DevBuf<double> gf;                 // 6 x stride: force / torque accumulated on ghosts (reverse communication)
+  double time = 0.0;                 // simulation time (steps x dt), drives the Lees-Edwards offset
+  DdCtx dd;                          // in-library domain decomposition (dd_host.cuh)
+  // lagged neighbor decision (sh_run): flag of step s-1 = "step s will exceed the skin"
+  int *h_lagflag = nullptr;          // pinned: [0..1] prediction ring, [2] skin violations
+  cudaEvent_t ev_lag[2] = {nullptr, nullptr};
+  int lag_slot = 0; bool lag_pending = false, lag_mode = true;
+  // optional per-step device timeline of the last sh_run ("step_trace" knob)
+  bool step_trace = false;
+  std::vector<cudaEvent_t> ev_step;
+  std::vector<float> step_ms;
+  std::vector<int> step_flags, step_flags_last;   // bit 0 neighbor rebuild, bit 1 cache build, bit 2 cache remap
   // neighbor
   DevBuf<int> cell_of, cell_count, cell_start, cell_fill, cell_atoms, tile_sum, cnt_full, cnt_half, nbr_off, half_off,
       nbr_j, pair_i, pair_j, pair_eij, pair_eji, pair_img, scalars;  // scalars: [0]=scan total [1]=rebuild flag [2]=work counter [3]/[4]=cache exhausted (hard/soft) [8]/[9]=list totals
@@ -370,6 +372,10 @@ int drain_events(sh_ctx *h) {
   return 0;
 }
 
+}  // namespace
+#include "dd_host.cuh"
+namespace {
+
 template <int NT>
 int launch_pair(sh_ctx *h, const PairArgs &A, int ctas_per_sm, size_t smem) {
   CU(cudaFuncSetAttribute(pair_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
@@ -515,8 +521,10 @@ int run_split_pipeline(sh_ctx *h, PairArgs &P) {
       // margin level: a cache that was used up quickly gets a wider margin, one that lived long a tighter one
       if (h->cache_level_pin >= 0) h->cache_level = h->cache_level_pin;
       else if (h->cache_exhausted) {
-        if (h->cache_age < 120 && h->cache_level < 2) h->cache_level++;
-        else if (h->cache_age > 1200 && h->cache_level > 0) h->cache_level--;
+        // (level 2 leaves no wider level for the pairs a neighbor rebuild adds, so every rebuild would be a full cache
+        // build: the adaptive choice stops at level 1; a full build costs about as much as 5 pair phases)
+        if (h->cache_age < 40 && h->cache_level < 1) h->cache_level++;
+        else if (h->cache_age > 400 && h->cache_level > 0) h->cache_level--;
       }
       h->cache_exhausted = false;
       if (h->cache_cap < (long long)np * 48) h->cache_cap = (long long)np * 48;
@@ -666,21 +674,64 @@ int prepare(sh_ctx *h) {
   return 0;
 }
 
+// tags on the host (sh_get_pairs, snapshots, sh_get_tags): refreshed lazily after the device moved atoms around
+int sync_tags_host(sh_ctx *h) {
+  if (h->tags_host_valid) return 0;
+  h->tag.resize(h->n);
+  if (h->n > 0) {
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(h->tag.data(), h->d_tag.p, (size_t)h->n * sizeof(long long), cudaMemcpyDeviceToHost));
+  }
+  h->tags_host_valid = true;
+  return 0;
+}
+
+// neighbor trigger: half the skin, less the distance the Lees-Edwards images have slid since the last build
+double neighbor_trigger(const sh_ctx *h) {
+  double t = 0.5 * h->skin;
+  if (h->dd.on && h->dd.le_rate != 0.0) t = std::max(0.0, 0.5 * (h->skin - std::fabs(h->dd.le_rate * h->dd.glen[1] * (h->time - h->dd.le_time_build))));
+  return t;
+}
+
+// all ranks must take the same rebuild decision: MAX over ranks of a device flag
+int reduce_flag(sh_ctx *h, int *d_flag) {
+  if (h->dd.on && h->dd.nranks > 1) NC(h->dd.nccl->AllReduce(d_flag, d_flag, 1, ncclInt, ncclMax, h->dd.comm, h->stream));
+  return 0;
+}
+
 int setup_forces(sh_ctx *h) {
   int rc;
   if ((rc = prepare(h))) return rc;
-  if (h->n > 0) {
-    const double trig = 0.5 * h->skin;
-    pose_kernel<<<cdiv(h->n, 256), 256, 0, h->stream>>>(view_all(h), h->d_shapes.p, h->list_valid ? trig * trig : -1.0, h->scalars.p + 1, 0, (int)h->n);
-    h->kernel_launches++;
+  const bool dd = h->dd.on;
+  bool fresh_borders = false;
+  if (dd) {
+    if (!h->dd.geometry_ok) { if ((rc = dd_setup_geometry(h))) return rc; }
+    if (!h->dd.borders_ok) { if ((rc = dd_borders(h))) return rc; fresh_borders = true; }
+    else if (h->list_valid) { if ((rc = dd_forward(h))) return rc; }
+  }
+  if (h->n > 0 || dd) {
+    const double trig = neighbor_trigger(h);
+    if (h->n > 0) {
+      pose_kernel<<<cdiv(h->n, 256), 256, 0, h->stream>>>(view_all(h), h->d_shapes.p, h->list_valid ? trig * trig : -1.0, h->scalars.p + 1, 0, (int)h->n);
+      h->kernel_launches++;
+    }
     bool rebuild = !h->list_valid;
     if (!rebuild) {
+      if ((rc = reduce_flag(h, h->scalars.p + 1))) return rc;
       CU(cudaMemcpyAsync(h->h_pinned + 4, h->scalars.p + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
       CU(cudaStreamSynchronize(h->stream));
       rebuild = h->h_pinned[4] != 0;
     }
+    if (rebuild && dd && !fresh_borders) {   // atoms moved since the borders were made: migrate, new ghosts, new poses
+      if ((rc = dd_rebuild(h))) return rc;
+      if (h->n > 0) {
+        pose_kernel<<<cdiv(h->n, 256), 256, 0, h->stream>>>(view_all(h), h->d_shapes.p, -1.0, h->scalars.p + 1, 0, (int)h->n);
+        h->kernel_launches++;
+      }
+    }
     if (rebuild) { if ((rc = build_neighbors(h))) return rc; }
   }
+  h->lag_pending = false;
   return compute_forces_device(h);
 }
 
@@ -712,6 +763,10 @@ int sh_create(sh_ctx **out, int device_id) {
   cudaMemset(h->scalars.p, 0, 16 * sizeof(int));
   cudaMemset(h->counters.p, 0, 16 * sizeof(unsigned long long));
   cudaMallocHost(&h->h_pinned, 64);
+  cudaMallocHost(&h->h_lagflag, 16 * sizeof(int));
+  std::memset(h->h_lagflag, 0, 16 * sizeof(int));
+  cudaMallocHost(&h->dd.h_int, 256 * sizeof(int));
+  for (auto &e : h->ev_lag) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
   cudaEventCreate(&h->run_e0); cudaEventCreate(&h->run_e1);
   h->ev.resize(2048); h->ev2.resize(4096); h->ev2_kind.resize(2048);
   for (auto &e : h->ev) cudaEventCreate(&e);
@@ -740,6 +795,19 @@ int sh_destroy(sh_ctx *h) {
   h->old_half_off.release(); h->old_pair_j.release(); h->fresh_list.release(); h->cache_count.release(); h->cc0.release(); h->cq0.release(); h->drift.release();
   if (h->h_pool_count) { cudaFreeHost(h->h_pool_count); cudaFreeHost(h->h_split_sc); cudaFreeHost(h->h_cache_invalid); cudaEventDestroy(h->ev_sc); }
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
+  if (h->h_lagflag) cudaFreeHost(h->h_lagflag);
+  if (h->dd.h_int) cudaFreeHost(h->dd.h_int);
+  for (auto &e : h->ev_lag) if (e) cudaEventDestroy(e);
+  for (auto &e : h->ev_step) cudaEventDestroy(e);
+  if (h->dd.comm && h->dd.nccl) h->dd.nccl->CommDestroy(h->dd.comm);
+  {
+    DdCtx &D = h->dd;
+    DevBuf<int> *ib2[] = {&D.flag, &D.pos, &D.order, &D.d_int, &D.send_idx, &D.send_slot, &D.shape2};
+    for (auto *b : ib2) b->release();
+    DevBuf<double> *db2[] = {&D.sendbuf, &D.recvbuf, &D.x2, &D.v2, &D.q2, &D.L2, &h->gf};
+    for (auto *b : db2) b->release();
+    D.tag2.release(); h->d_tag.release();
+  }
   h->stage.release();
   cudaEventDestroy(h->run_e0); cudaEventDestroy(h->run_e1);
   cudaStreamDestroy(h->stream);
@@ -752,6 +820,9 @@ const char *sh_last_error(const sh_ctx *h) { return h ? h->err.c_str() : "null h
 int sh_set_box(sh_ctx *h, const double lo[3], const double hi[3], const int periodic[3]) {
   for (int d = 0; d < 3; d++) if (!(hi[d] > lo[d])) return fail(h, "box: hi <= lo");
   for (int d = 0; d < 3; d++) { h->lo[d] = lo[d]; h->hi[d] = hi[d]; h->periodic[d] = periodic[d] != 0; }
+  // with the domain decomposition on this is the GLOBAL box; the engine-local periodic flags follow from the brick grid
+  for (int d = 0; d < 3; d++) { h->dd.glo[d] = lo[d]; h->dd.ghi[d] = hi[d]; h->dd.gper[d] = periodic[d] != 0; }
+  h->dd.geometry_ok = false; h->dd.borders_ok = false;
   h->box_set = true; h->forces_valid = false; h->list_valid = false;
   return 0;
 }
@@ -796,50 +867,79 @@ int sh_get_nodes(const sh_ctx *h, int shape, double *p, double *nds) {
   return 0;
 }
 
-int sh_set_atoms(sh_ctx *h, int64_t n, const int64_t *tag, const int *shape, const double *x, const double *v,
-                 const double *quat, const double *angmom) {
-  if (n < 0 || n > (int64_t)1 << 30) return fail(h, "bad atom count");
-  if (n > 0 && (!shape || !x)) return fail(h, "shape and x are required");
+int sh_set_atoms(sh_ctx *h, int64_t n_in, const int64_t *tag_in, const int *shape_in, const double *x_in, const double *v_in,
+                 const double *quat_in, const double *angmom_in) {
+  if (n_in < 0 || n_in > (int64_t)1 << 30) return fail(h, "bad atom count");
+  if (n_in > 0 && (!shape_in || !x_in)) return fail(h, "shape and x are required");
   const int ns = (int)h->shapes.size();
-  for (int64_t i = 0; i < n; i++) if (shape[i] < 0 || shape[i] >= ns) return fail(h, "atom shape id out of range");
+  for (int64_t i = 0; i < n_in; i++) if (shape_in[i] < 0 || shape_in[i] >= ns) return fail(h, "atom shape id out of range");
+  if (quat_in) for (int64_t i = 0; i < n_in; i++) {
+    const double *q = quat_in + 4 * i;
+    if (!(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3] > 0)) return fail(h, "zero quaternion");
+  }
   CU(cudaSetDevice(h->device));
-  const int st = (int)((n + 31) / 32 * 32) + 32;
+  // domain decomposition: every rank is handed the same atoms (like create_atoms / read_data) and keeps the ones inside
+  // its brick, wrapped into the global box
+  std::vector<int64_t> keep;
+  std::vector<double> xw, vw;
+  const bool dd = h->dd.on;
+  if (dd) {
+    int rc;
+    if ((rc = dd_setup_geometry(h))) return rc;
+    dd_refresh_shifts(h);
+    const DdGeom &G = h->dd.G;
+    xw.assign(x_in, x_in + 3 * n_in);
+    if (v_in) vw.assign(v_in, v_in + 3 * n_in); else vw.assign(3 * n_in, 0.0);
+    for (int64_t i = 0; i < n_in; i++) {
+      double *x = &xw[3 * i];
+      if (G.gper[1]) {
+        const double ny = std::floor((x[1] - G.glo[1]) / G.L[1]);
+        if (ny != 0.0) { x[1] -= G.L[1] * ny; x[0] -= ny * G.le_offset; vw[3 * i] -= ny * G.le_vshear; }
+      }
+      if (G.gper[0]) x[0] -= G.L[0] * std::floor((x[0] - G.glo[0]) / G.L[0]);
+      if (G.gper[2]) x[2] -= G.L[2] * std::floor((x[2] - G.glo[2]) / G.L[2]);
+      int gi[3];
+      for (int d = 0; d < 3; d++) { const int c = (int)std::floor((x[d] - G.glo[d]) / G.sub[d]); gi[d] = std::min(std::max(c, 0), G.pgrid[d] - 1); }
+      if ((gi[0] * G.pgrid[1] + gi[1]) * G.pgrid[2] + gi[2] == h->dd.rank) keep.push_back(i);
+    }
+  }
+  const int64_t n = dd ? (int64_t)keep.size() : n_in;
+  const double *x = dd ? xw.data() : x_in, *v = dd ? vw.data() : v_in;
+  auto src_index = [&](int64_t i) -> int64_t { return dd ? keep[i] : i; };
+  const int st = (int)((n + (dd ? std::max<int64_t>(n / 4, 1024) : 0) + 31) / 32 * 32) + 32;
   try {
     h->x.ensure(3 * (size_t)st); h->v.ensure(3 * (size_t)st); h->q.ensure(4 * (size_t)st); h->L.ensure(3 * (size_t)st);
-    h->f.ensure(3 * (size_t)st); h->tq.ensure(3 * (size_t)st); h->c.ensure(3 * (size_t)st); h->Rs.ensure(9 * (size_t)st);
-    h->c0.ensure(3 * (size_t)st); h->wallf.ensure(6 * (size_t)st); h->ewall.ensure(st); h->ke.ensure(2 * (size_t)st);
-    h->shape.ensure(st); h->cc0.ensure(3 * (size_t)st); h->cq0.ensure(4 * (size_t)st);
+    h->shape.ensure(st); h->d_tag.ensure(st);
   } catch (std::string &e) { return fail(h, e); }
+  { int rc = dd_ensure_derived(h, st); if (rc) return rc; }
   h->n = n; h->stride = st;
   std::vector<double> buf((size_t)4 * st, 0.0);
   auto up = [&](DevBuf<double> &dst, const double *src, int ncomp, bool is_quat) -> cudaError_t {
     std::fill(buf.begin(), buf.end(), 0.0);
     for (int64_t i = 0; i < n; i++) {
+      const int64_t k = src_index(i);
       if (src) {
         double nn = 1.0;
-        if (is_quat) {
-          nn = std::sqrt(src[4 * i] * src[4 * i] + src[4 * i + 1] * src[4 * i + 1] + src[4 * i + 2] * src[4 * i + 2] + src[4 * i + 3] * src[4 * i + 3]);
-        }
-        for (int d = 0; d < ncomp; d++) buf[(size_t)d * st + i] = is_quat ? src[ncomp * i + d] / nn : src[ncomp * i + d];
+        if (is_quat) nn = std::sqrt(src[4 * k] * src[4 * k] + src[4 * k + 1] * src[4 * k + 1] + src[4 * k + 2] * src[4 * k + 2] + src[4 * k + 3] * src[4 * k + 3]);
+        for (int d = 0; d < ncomp; d++) buf[(size_t)d * st + i] = is_quat ? src[ncomp * k + d] / nn : src[ncomp * k + d];
       } else if (is_quat) buf[i] = 1.0;
     }
     return cudaMemcpy(dst.p, buf.data(), (size_t)ncomp * st * sizeof(double), cudaMemcpyHostToDevice);
   };
-  if (quat) for (int64_t i = 0; i < n; i++) {
-    double nn = quat[4 * i] * quat[4 * i] + quat[4 * i + 1] * quat[4 * i + 1] + quat[4 * i + 2] * quat[4 * i + 2] + quat[4 * i + 3] * quat[4 * i + 3];
-    if (!(nn > 0)) return fail(h, "zero quaternion");
-  }
-  CU(up(h->x, x, 3, false)); CU(up(h->v, v, 3, false)); CU(up(h->q, quat, 4, true)); CU(up(h->L, angmom, 3, false));
+  CU(up(h->x, x, 3, false)); CU(up(h->v, v, 3, false)); CU(up(h->q, quat_in, 4, true)); CU(up(h->L, angmom_in, 3, false));
   CU(cudaMemset(h->f.p, 0, 3 * (size_t)st * 8)); CU(cudaMemset(h->tq.p, 0, 3 * (size_t)st * 8));
   CU(cudaMemset(h->wallf.p, 0, 6 * (size_t)st * 8)); CU(cudaMemset(h->ewall.p, 0, (size_t)st * 8));
   CU(cudaMemset(h->c0.p, 0, 3 * (size_t)st * 8));
   std::vector<int> sh(st, 0);
-  for (int64_t i = 0; i < n; i++) sh[i] = shape[i];
+  for (int64_t i = 0; i < n; i++) sh[i] = shape_in[src_index(i)];
   CU(cudaMemcpy(h->shape.p, sh.data(), (size_t)st * sizeof(int), cudaMemcpyHostToDevice));
   h->tag.resize(n);
-  for (int64_t i = 0; i < n; i++) h->tag[i] = tag ? tag[i] : i + 1;
+  for (int64_t i = 0; i < n; i++) h->tag[i] = tag_in ? tag_in[src_index(i)] : src_index(i) + 1;
+  if (n > 0) CU(cudaMemcpy(h->d_tag.p, h->tag.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice));
+  h->tags_host_valid = true;
   h->forces_valid = false; h->list_valid = false; h->npairs = 0; h->nentries = 0; h->nghost = 0;
   h->atoms_epoch++; h->cache_state = CACHE_INVALID;
+  h->dd.borders_ok = false;
   return 0;
 }
 
@@ -900,43 +1000,30 @@ int sh_compute_forces(sh_ctx *h) {
 }
 
 // ---- one timestep in two halves, so that a multi-rank driver can put the ghost exchange between them
-int sh_step_begin(sh_ctx *h, int *rebuild_wanted) {
-  CU(cudaSetDevice(h->device));
-  int rc;
-  if (!h->forces_valid || !h->list_valid) { if ((rc = setup_forces(h))) return rc; }
+namespace {
+int launch_integrate_initial(sh_ctx *h, int check_violation) {
   const int n = (int)(h->n - h->nghost);
-  if (rebuild_wanted) *rebuild_wanted = 0;
-  if (h->n == 0) return 0;
-  const double trig = 0.5 * h->skin, trig2 = trig * trig;
+  const double trig = neighbor_trigger(h), trig2 = trig * trig;
   const double damp_v = 1.0 - 0.5 * h->dt * h->gamma_lin, damp_L = 1.0 - 0.5 * h->dt * h->gamma_rot;
-  int *d_flag = h->scalars.p + 1;
   if (n > 0) {
-    integrate_initial_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(view(h), h->d_shapes.p, h->dt, h->g[0], h->g[1], h->g[2], trig2, d_flag, damp_v, damp_L);
+    integrate_initial_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(view(h), h->d_shapes.p, h->dt, h->g[0], h->g[1], h->g[2], trig2, h->scalars.p, damp_v, damp_L, check_violation);
     h->kernel_launches++;
   }
+  h->time += h->dt;
   h->steps_since_build++;
-  bool rebuild = false;
-  if (h->steps_since_build >= h->neigh_every) {
-    if (h->neigh_check) {
-      CU(cudaMemcpyAsync(h->h_pinned + 4, d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-      CU(cudaStreamSynchronize(h->stream));
-      rebuild = h->h_pinned[4] != 0;
-    } else rebuild = true;
-  }
-  if (rebuild_wanted) *rebuild_wanted = rebuild ? 1 : 0;
   return 0;
 }
 
-int sh_step_end(sh_ctx *h, int rebuild) {
-  CU(cudaSetDevice(h->device));
+int step_finish(sh_ctx *h, int rebuild) {
   int rc;
-  if (h->n == 0) return 0;
   const int n = (int)(h->n - h->nghost);
   const double damp_v = 1.0 - 0.5 * h->dt * h->gamma_lin, damp_L = 1.0 - 0.5 * h->dt * h->gamma_rot;
   if (!h->list_valid) {  // atoms were re-set mid-step (migration): poses of all atoms
     if ((rc = prepare(h))) return rc;
-    pose_kernel<<<cdiv(h->n, 256), 256, 0, h->stream>>>(view_all(h), h->d_shapes.p, -1.0, h->scalars.p + 1, 0, (int)h->n);
-    h->kernel_launches++;
+    if (h->n > 0) {
+      pose_kernel<<<cdiv(h->n, 256), 256, 0, h->stream>>>(view_all(h), h->d_shapes.p, -1.0, h->scalars.p + 1, 0, (int)h->n);
+      h->kernel_launches++;
+    }
   } else if (h->nghost > 0) {   // ghost poses from the freshly received x / quat
     pose_kernel<<<cdiv(h->nghost, 256), 256, 0, h->stream>>>(view_all(h), h->d_shapes.p, -1.0, h->scalars.p + 1, n, (int)h->nghost);
     h->kernel_launches++;
@@ -950,21 +1037,107 @@ int sh_step_end(sh_ctx *h, int rebuild) {
   return 0;
 }
 
+// One full timestep of sh_run.  With the lagged neighbor decision (default) the host never waits for the step it is
+// enqueuing: whether step s rebuilds was predicted by the integrator of step s-1 (sc[5]) and arrives through a pinned
+// slot + event; a misprediction is counted (sc[6]) and reported as an error by sh_run.
+int step_once(sh_ctx *h) {
+  int rc;
+  const bool dd = h->dd.on;
+  const bool due = h->steps_since_build + 1 >= h->neigh_every;
+  const bool lag = h->lag_mode && h->neigh_check;
+  int rebuild = 0;
+  bool decided = false;
+  if (!due) decided = true;
+  else if (!h->neigh_check) { rebuild = 1; decided = true; }
+  if (lag) {
+    int pred = 0;
+    if (h->lag_pending) { CU(cudaEventSynchronize(h->ev_lag[h->lag_slot])); pred = h->h_lagflag[h->lag_slot]; h->lag_pending = false; }
+    if (!decided) { rebuild = pred; decided = true; }
+  }
+  if ((rc = launch_integrate_initial(h, decided && !rebuild))) return rc;
+  if (!decided) {   // classic decision: this step's own displacement flag, one host round trip
+    if ((rc = reduce_flag(h, h->scalars.p + 1))) return rc;
+    CU(cudaMemcpyAsync(h->h_pinned + 4, h->scalars.p + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    rebuild = h->h_pinned[4] != 0;
+  }
+  if (lag) {
+    if (!rebuild) {   // a prediction made on a rebuild step refers to the old origins: dropped
+      if ((rc = reduce_flag(h, h->scalars.p + 5))) return rc;
+      h->lag_slot ^= 1;
+      CU(cudaMemcpyAsync(h->h_lagflag + h->lag_slot, h->scalars.p + 5, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaEventRecord(h->ev_lag[h->lag_slot], h->stream));
+      h->lag_pending = true;
+    }
+    CU(cudaMemsetAsync(h->scalars.p + 5, 0, sizeof(int), h->stream));
+  }
+  if (dd) { if ((rc = rebuild ? dd_rebuild(h) : dd_forward(h))) return rc; }
+  return step_finish(h, rebuild);
+}
+}  // namespace
+
+int sh_step_begin(sh_ctx *h, int *rebuild_wanted) {
+  CU(cudaSetDevice(h->device));
+  int rc;
+  if (!h->forces_valid || !h->list_valid) { if ((rc = setup_forces(h))) return rc; }
+  if (rebuild_wanted) *rebuild_wanted = 0;
+  if (h->n == 0) return 0;
+  const bool due = h->steps_since_build + 1 >= h->neigh_every;
+  if ((rc = launch_integrate_initial(h, 0))) return rc;
+  h->lag_pending = false;
+  bool rebuild = false;
+  if (due) {
+    if (h->neigh_check) {
+      CU(cudaMemcpyAsync(h->h_pinned + 4, h->scalars.p + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+      rebuild = h->h_pinned[4] != 0;
+    } else rebuild = true;
+  }
+  if (rebuild_wanted) *rebuild_wanted = rebuild ? 1 : 0;
+  return 0;
+}
+
+int sh_step_end(sh_ctx *h, int rebuild) {
+  CU(cudaSetDevice(h->device));
+  if (h->n == 0) return 0;
+  return step_finish(h, rebuild);
+}
+
 int sh_run(sh_ctx *h, int64_t nsteps) {
   CU(cudaSetDevice(h->device));
   int rc;
   if (!h->forces_valid || !h->list_valid) { if ((rc = setup_forces(h))) return rc; }
-  if (h->n == 0) return 0;
+  if (h->n == 0 && !h->dd.on) return 0;
   CU(cudaEventRecord(h->run_e0, h->stream));
-  for (int64_t step = 0; step < nsteps; step++) {
-    int rebuild = 0;
-    if ((rc = sh_step_begin(h, &rebuild))) return rc;
-    if ((rc = sh_step_end(h, rebuild))) return rc;
+  const bool trace = h->step_trace && nsteps <= 4096;
+  if (trace) {
+    while ((int64_t)h->ev_step.size() < nsteps + 1) { cudaEvent_t e; CU(cudaEventCreate(&e)); h->ev_step.push_back(e); }
+    CU(cudaEventRecord(h->ev_step[0], h->stream));
+    h->step_flags.assign(nsteps, 0);
   }
+  for (int64_t step = 0; step < nsteps; step++) {
+    const int64_t nb0 = h->neighbor_builds, cb0 = h->cache_builds, cr0 = h->cache_remaps;
+    if ((rc = step_once(h))) return rc;
+    if (trace) {
+      CU(cudaEventRecord(h->ev_step[step + 1], h->stream));
+      h->step_flags[step] = (h->neighbor_builds > nb0 ? 1 : 0) | (h->cache_builds > cb0 ? 2 : 0) | (h->cache_remaps > cr0 ? 4 : 0);
+    }
+  }
+  CU(cudaMemcpyAsync(h->h_lagflag + 2, h->scalars.p + 6, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaEventRecord(h->run_e1, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaGetLastError());
   { float ms = 0; cudaEventElapsedTime(&ms, h->run_e0, h->run_e1); h->sec_run_last = ms * 1e-3; h->sec_run_total += h->sec_run_last; }
+  if (trace) {
+    h->step_ms.assign(nsteps, 0.f);
+    for (int64_t k = 0; k < nsteps; k++) cudaEventElapsedTime(&h->step_ms[k], h->ev_step[k], h->ev_step[k + 1]);
+    h->step_flags_last = h->step_flags;
+  } else h->step_ms.clear();
+  if (h->h_lagflag[2] != 0) {
+    CU(cudaMemset(h->scalars.p + 6, 0, sizeof(int)));
+    return fail(h, "neighbor skin violated: an atom moved more than half the skin on a step the lagged neighbor decision did not "
+                   "rebuild on (increase the skin, or sh_set_tuning \"sync_rebuild\" 1)");
+  }
   return 0;
 }
 
@@ -1070,6 +1243,7 @@ struct SnapHeader { char magic[8]; int32_t version, nshapes; int64_t n, step; do
 int sh_write_snapshot(const sh_ctx *hc, const char *path, int64_t step) {
   sh_ctx *h = const_cast<sh_ctx *>(hc);
   const int64_t n = h->n - h->nghost;
+  { int rc = sync_tags_host(h); if (rc) return rc; }
   std::vector<double> x(3 * n), v(3 * n), q(4 * n), L(3 * n);
   if (n > 0) { int rc = sh_get_atoms(h, n, x.data(), v.data(), q.data(), L.data(), nullptr, nullptr); if (rc) return rc; }
   std::vector<int> shp(h->stride > 0 ? h->stride : 1);
@@ -1079,7 +1253,7 @@ int sh_write_snapshot(const sh_ctx *hc, const char *path, int64_t step) {
   SnapHeader hd{};
   std::memcpy(hd.magic, "SHGPUSNP", 8);
   hd.version = 1; hd.nshapes = (int)h->shapes.size(); hd.n = n; hd.step = step;
-  for (int d = 0; d < 3; d++) { hd.lo[d] = h->lo[d]; hd.hi[d] = h->hi[d]; hd.periodic[d] = h->periodic[d]; }
+  for (int d = 0; d < 3; d++) { hd.lo[d] = h->dd.glo[d]; hd.hi[d] = h->dd.ghi[d]; hd.periodic[d] = h->dd.gper[d]; }   // the global box
   bool ok = fwrite(&hd, sizeof hd, 1, f) == 1;
   ok = ok && (n == 0 || (fwrite(h->tag.data(), sizeof(int64_t), n, f) == (size_t)n && fwrite(shp.data(), sizeof(int), n, f) == (size_t)n &&
                          fwrite(x.data(), 8, 3 * n, f) == (size_t)(3 * n) && fwrite(v.data(), 8, 3 * n, f) == (size_t)(3 * n) &&
@@ -1139,6 +1313,7 @@ int sh_get_pairs(const sh_ctx *hc, int64_t cap, int64_t *npairs, int64_t *tag_i,
   CU(cudaStreamSynchronize(h->stream));
   const int np = h->forces_valid ? h->npairs : 0;
   if (npairs) *npairs = np;
+  { int rc = sync_tags_host(h); if (rc) return rc; }
   const int m = (int)std::min<int64_t>(np, cap);
   if (m <= 0) return 0;
   std::vector<int> pi(m), pj(m);
@@ -1310,7 +1485,10 @@ int sh_set_tuning(sh_ctx *h, const char *key, double value) {
     if (!h->shapes.empty()) return fail(h, "cube_n must be set before add_shape");
     if (v != 0 && (v < 8 || v > 144)) return fail(h, "cube_n must be 0 (default) or 8..144");
     h->cube_n = v;
-  } else return fail(h, "unknown tuning key: " + k);
+  } else if (k == "step_trace") { h->step_trace = v != 0; }
+  else if (k == "dd_self_ghosts") { h->dd.self_ghosts = v != 0; h->dd.geometry_ok = false; h->dd.borders_ok = false; }
+  else if (k == "sync_rebuild") { h->lag_mode = v == 0; h->lag_pending = false; }
+  else return fail(h, "unknown tuning key: " + k);
   return 0;
 }
 
@@ -1338,6 +1516,81 @@ int sh_measure_fp64_peak(sh_ctx *h, double *flops_per_s, double *sm_clock_mhz_es
   if (flops_per_s) *flops_per_s = best;
   if (sm_clock_mhz_est) *sm_clock_mhz_est = best / (2.0 * 64.0 * h->sm_count) * 1e-6;  // if 64 FP64 lanes/SM
   CU(cudaGetLastError());
+  return 0;
+}
+
+// ---- multi-GPU behind the C ABI: one handle per rank; NCCL inside the library ------------------------
+int sh_dd_unique_id(char *id, int cap) {
+  if (!id || cap < (int)sizeof(ncclUniqueId)) return -1;
+  NcclApi *api = nccl_api();
+  if (!api) return -8;
+  ncclUniqueId u;
+  if (api->GetUniqueId(&u) != ncclSuccess) return -9;
+  std::memcpy(id, &u, sizeof u);
+  return 0;
+}
+
+int sh_dd_init(sh_ctx *h, int rank, int nranks, const char *id, const int *pgrid) {
+  if (!h) return -1;
+  if (nranks < 1 || nranks > DD_MAX_RANKS || rank < 0 || rank >= nranks) return fail(h, "dd_init: bad rank / nranks (at most 64 ranks)");
+  if (h->dd.on) return fail(h, "dd_init: already initialised");
+  CU(cudaSetDevice(h->device));
+  DdCtx &D = h->dd;
+  D.rank = rank; D.nranks = nranks;
+  if (nranks > 1) {
+    if (!id) return fail(h, "dd_init: a unique id is required for more than one rank");
+    D.nccl = nccl_api();
+    if (!D.nccl) return fail(h, "dd_init: NCCL is not available (libnccl.so.2)");
+    ncclUniqueId u;
+    std::memcpy(&u, id, sizeof u);
+    NC(D.nccl->CommInitRank(&D.comm, nranks, u, rank));
+  }
+  if (pgrid && pgrid[0] > 0 && pgrid[1] > 0 && pgrid[2] > 0) { for (int d = 0; d < 3; d++) D.pgrid[d] = pgrid[d]; D.pgrid_set = true; }
+  D.on = true; D.geometry_ok = false; D.borders_ok = false;
+  h->forces_valid = false; h->list_valid = false;
+  if (h->n > 0) return fail(h, "dd_init must precede sh_set_atoms");
+  return 0;
+}
+
+int sh_dd_get_info(const sh_ctx *hc, int pgrid[3], int brick[3], int64_t *nlocal, int64_t *nghost, int64_t *migrated,
+                   int64_t *border_builds) {
+  sh_ctx *h = const_cast<sh_ctx *>(hc);
+  if (!h) return -1;
+  if (pgrid) for (int d = 0; d < 3; d++) pgrid[d] = h->dd.pgrid[d];
+  if (brick) for (int d = 0; d < 3; d++) brick[d] = h->dd.g[d];
+  if (nlocal) *nlocal = h->n - h->nghost;
+  if (nghost) *nghost = h->nghost;
+  if (migrated) *migrated = h->dd.migrated_out;
+  if (border_builds) *border_builds = h->dd.border_builds;
+  return 0;
+}
+
+int sh_get_step_trace(const sh_ctx *h, int64_t cap, int64_t *nsteps, double *ms, int *flags) {
+  if (!h) return -1;
+  const int64_t n = (int64_t)h->step_ms.size();
+  if (nsteps) *nsteps = n;
+  for (int64_t k = 0; k < std::min(n, cap); k++) { if (ms) ms[k] = h->step_ms[k]; if (flags) flags[k] = h->step_flags_last[k]; }
+  return 0;
+}
+
+int sh_get_tags(const sh_ctx *hc, int64_t n, int64_t *tags) {
+  sh_ctx *h = const_cast<sh_ctx *>(hc);
+  if (n < 0 || n > h->n) return fail(h, "get_tags: n out of range");
+  CU(cudaSetDevice(h->device));
+  int rc = sync_tags_host(h);
+  if (rc) return rc;
+  for (int64_t i = 0; i < n; i++) tags[i] = h->tag[i];
+  return 0;
+}
+
+// Lees-Edwards shear (fix deform xy ... remap v): flow along x, gradient along y, rate = d(v_x)/dy.  Images across the
+// periodic y boundary are ghosts displaced by rate * Ly * t along x; uses the decomposition machinery even on one GPU.
+int sh_set_shear(sh_ctx *h, double rate) {
+  if (!h) return -1;
+  if (h->n > 0) return fail(h, "set_shear must precede sh_set_atoms");
+  if (!h->dd.on) { int rc = sh_dd_init(h, 0, 1, nullptr, nullptr); if (rc) return rc; }
+  h->dd.le_rate = rate; h->dd.le_off_build = 0.0; h->dd.le_time_build = h->time;
+  h->dd.geometry_ok = false; h->dd.borders_ok = false;
   return 0;
 }
 

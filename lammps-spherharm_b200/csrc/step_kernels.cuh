@@ -170,8 +170,12 @@ __device__ __forceinline__ void qnormalize(double q[4]) {
 }
 
 // first half of velocity-Verlet + Richardson quaternion step + pose + displacement flag
+// sc = the context's device scalars: sc[1] classic rebuild flag (displacement since the last build > trigger), sc[5]
+// PREDICTION for the next step (displacement + twice this step's own move > trigger: the host decides one step ahead and
+// never waits for the device), sc[6] skin violations (the displacement exceeded the trigger on a step the host had
+// already decided not to rebuild on).
 __global__ void integrate_initial_kernel(AtomView A, const DevShape *shapes, double dt, double g0, double g1,
-                                         double g2, double trigger2, int *rebuild_flag, double damp_v, double damp_L) {
+                                         double g2, double trigger2, int *sc, double damp_v, double damp_L, int check_violation) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= A.n) return;
   const int st = A.stride;
@@ -214,14 +218,18 @@ __global__ void integrate_initial_kernel(AtomView A, const DevShape *shapes, dou
   pose_of(s, q, xx, Rs, c);
 #pragma unroll
   for (int e = 0; e < 9; e++) A.Rs[e * st + i] = Rs[e];
-  double disp2 = 0;
+  double disp2 = 0, step2 = 0;
 #pragma unroll
   for (int d = 0; d < 3; d++) {
+    const double ds = c[d] - A.c[d * st + i];
+    step2 += ds * ds;
     A.c[d * st + i] = c[d];
     const double dd = c[d] - A.c0[d * st + i];
     disp2 += dd * dd;
   }
-  if (disp2 > trigger2) *rebuild_flag = 1;
+  if (disp2 > trigger2) { sc[1] = 1; if (check_violation) atomicAdd(&sc[6], 1); }
+  const double ahead = sqrt(disp2) + 2.0 * sqrt(step2);
+  if (ahead * ahead > trigger2) sc[5] = 1;
 }
 
 __global__ void integrate_final_kernel(AtomView A, const DevShape *shapes, double dt, double g0, double g1,

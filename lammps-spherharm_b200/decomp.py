@@ -285,3 +285,44 @@ class DomainDecomposition:
         for k in fields:
             out[k] = allr[:, o:o + ncol[k]]; o += ncol[k]
         return out
+
+
+# ---------------------------------------------------------------------- in-library decomposition (NCCL inside libshgpu)
+def native_engine(pkg, cfg, device, tuning=None, pgrid=None, shear=0.0):
+    """One engine per rank whose decomposition (migration, borders, ghost exchange) runs inside libshgpu (sh_dd_*).
+    torch.distributed only carries the 128-byte NCCL id from rank 0 to the others."""
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    uid = [pkg.ShGpu.dd_unique_id() if (rank == 0 and world > 1) else None]
+    if world > 1:
+        dist.broadcast_object_list(uid, src=0)
+    sim = pkg.ShGpu(device=device)
+    for k, v in (tuning or {}).items():
+        sim.set_tuning(k, v)
+    sim.dd_init(rank, world, uid[0], pgrid)
+    if shear:
+        sim.set_shear(shear)
+    pkg.workloads.apply(sim, cfg)
+    return sim
+
+
+def gather_owned_native(sim, fields=("x", "v", "quat", "angmom", "f", "torque")):
+    """Owned atoms of every rank, sorted by tag, on rank 0 (tests / output)."""
+    info = sim.dd_info()
+    nl = info["nlocal"]
+    st = sim.get_atoms(fields)
+    mine = {k: st[k][:nl] for k in fields}
+    mine["tag"] = sim.get_tags()[:nl]
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        parts = [None] * dist.get_world_size()
+        dist.all_gather_object(parts, mine)
+        if dist.get_rank() != 0:
+            return None
+    else:
+        parts = [mine]
+    tag = np.concatenate([p["tag"] for p in parts])
+    order = np.argsort(tag, kind="stable")
+    out = {"tag": tag[order]}
+    for k in fields:
+        out[k] = np.concatenate([p[k] for p in parts], axis=0)[order]
+    return out
