@@ -477,10 +477,9 @@ def run_graft(args):
         line["migrated_atoms_per_rank"] = dd_info["migrated"]
         if cpu:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line))
     if use_dist:
         dist.destroy_process_group()
-    return 0
+    return line if rank == 0 else None
 
 
 def strong_case(args, pkg, torch, dist, use_dist, local, world, rank, allsum):
@@ -550,7 +549,22 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "graft":
         args.warmup = 3
-    return run_reference(args) if args.impl == "reference" else run_graft(args)
+    if args.impl == "reference":
+        return run_reference(args)
+    # stdout carries exactly ONE line, the JSON: anything a library prints on fd 1 meanwhile (NCCL's version banner when the
+    # communicator inside libshgpu comes up) goes to stderr
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = run_graft(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    return 0
 
 
 if __name__ == "__main__":

@@ -58,7 +58,7 @@ def build_host(force=False):
     if not force and os.path.exists(SHLMP) and os.path.getmtime(SHLMP) > max(os.path.getmtime(src), os.path.getmtime(SO)):
         return SHLMP
     gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
-    cmd = [gxx, "-O2", "-std=c++17", "-o", SHLMP, src, "-L" + HERE, "-lshgpu", "-Wl,-rpath,$ORIGIN"]
+    cmd = [gxx, "-O2", "-std=c++17", "-pthread", "-o", SHLMP, src, "-L" + HERE, "-lshgpu", "-Wl,-rpath,$ORIGIN"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)

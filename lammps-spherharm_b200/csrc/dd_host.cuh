@@ -245,7 +245,7 @@ int dd_migrate(sh_ctx *h) {
   int nmig = 0, narr = 0;
   for (int k = 0; k < nmr; k++) { sc[k] = D.h_int[64 + k]; rc[k] = D.h_int[96 + k]; nmig += sc[k]; narr += rc[k]; }
   if (nown > 0 && nstay + nmig != nown) return fail(h, "domain decomposition: migration counts are inconsistent");
-  D.migrated_out += nmig; D.migrated_in += narr;
+  D.migrated_out += nmig; D.migrated_in += narr; D.last_nstay = nstay;
   try { D.sendbuf.ensure((size_t)DD_MIGREC * std::max(nmig, 1)); D.recvbuf.ensure((size_t)DD_MIGREC * std::max(narr, 1)); }
   catch (std::string &e) { return fail(h, e); }
   if (nmig > 0) {

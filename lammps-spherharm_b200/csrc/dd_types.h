@@ -43,7 +43,7 @@ struct DdCtx {
   DevBuf<int> flag, pos, order, d_int, send_idx, send_slot, shape2;
   DevBuf<double> sendbuf, recvbuf, x2, v2, q2, L2;
   DevBuf<long long> tag2;
-  int stride2 = 0;
+  int stride2 = 0, last_nstay = 0;
   int *h_int = nullptr;                          // pinned, 256 ints
   int64_t migrated_out = 0, migrated_in = 0, border_builds = 0;
 };

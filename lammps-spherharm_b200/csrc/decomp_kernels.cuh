@@ -189,4 +189,56 @@ __global__ void dd_unpack_kernel(AtomView A, long long *tag, int first, int m, i
   }
 }
 
+// ---- candidate-cache carry-over across a decomposed rebuild ---------------------------------------------------------
+__device__ __forceinline__ unsigned dd_hash_tag(long long t) {
+  unsigned long long z = (unsigned long long)t * 0x9E3779B97F4A7C15ull;
+  return (unsigned)(z >> 32);
+}
+// open-addressing table of the OLD ghosts (entries = old atom index, -1 = empty), keyed by tag; several images of one
+// atom may be present
+__global__ void dd_ghost_hash_kernel(const long long *old_tag, int nown, int nghost, int *table, int hs) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nghost) return;
+  const int e = nown + k;
+  unsigned slot = dd_hash_tag(old_tag[e]) & (unsigned)(hs - 1);
+  while (atomicCAS(&table[slot], -1, e) != -1) slot = (slot + 1) & (unsigned)(hs - 1);
+}
+// new atom -> old atom: owned stayers through the compaction order, arrivals are new (-1), ghosts through the tag hash +
+// proximity of the origin (images of one atom are a box length apart).  The cache's reference state (origin and
+// quaternion at the last cache build) follows the atom; a new atom starts from its current state.
+__global__ void dd_cache_map_kernel(AtomView A, const long long *tag, int nown, int nstay, const int *order, const long long *old_tag,
+                                    const double *old_c, int old_stride, int old_nown, int old_n, const int *table, int hs, double near2,
+                                    const double *old_cc0, const double *old_cq0, int *amap) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= A.n) return;
+  const int st = A.stride;
+  int o = -1;
+  if (a < nown) { if (a < nstay) o = order[a]; }
+  else {
+    const long long t = tag[a];
+    unsigned slot = dd_hash_tag(t) & (unsigned)(hs - 1);
+    for (int probe = 0; probe < hs; probe++) {
+      const int e = table[slot];
+      if (e < 0) break;
+      if (old_tag[e] == t) {
+        const double d0 = A.c[a] - old_c[e], d1 = A.c[st + a] - old_c[old_stride + e], d2 = A.c[2 * st + a] - old_c[2 * old_stride + e];
+        if (d0 * d0 + d1 * d1 + d2 * d2 < near2) { o = e; break; }
+      }
+      slot = (slot + 1) & (unsigned)(hs - 1);
+    }
+  }
+  amap[a] = o;
+  if (o >= 0) {
+#pragma unroll
+    for (int d = 0; d < 3; d++) A.cc0[d * st + a] = old_cc0[d * old_stride + o];
+#pragma unroll
+    for (int d = 0; d < 4; d++) A.cq0[d * st + a] = old_cq0[d * old_stride + o];
+  } else {
+#pragma unroll
+    for (int d = 0; d < 3; d++) A.cc0[d * st + a] = A.c[d * st + a];
+#pragma unroll
+    for (int d = 0; d < 4; d++) A.cq0[d * st + a] = A.q[d * st + a];
+  }
+}
+
 }  // namespace shgpu

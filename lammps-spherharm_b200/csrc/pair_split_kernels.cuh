@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(WPB * 32) pair_cache_build_kernel(PairArgs A, 
 // are built by pair_cache_build_kernel with the next larger margin (they start from a state that may already have used
 // up half of the current one).  One thread per new pair; the pool space of a warp is allocated with one atomic.
 __global__ void cache_remap_kernel(PairArgs A, const int *old_half_off, const int *old_pair_j, int old_nown, const PairHot *old_hot,
-                                   const unsigned short *old_pool, CacheArgs C, int *fresh_list, int *nfresh) {
+                                   const unsigned short *old_pool, CacheArgs C, int *fresh_list, int *nfresh, const int *amap) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   int ntot = 0, q = -1;
@@ -316,12 +316,16 @@ __global__ void cache_remap_kernel(PairArgs A, const int *old_half_off, const in
   hrec.i = hrec.j = 0; hrec.n0 = hrec.n1 = 0; hrec.off = 0; hrec.img = 0; hrec.shp_i = hrec.shp_j = 0; hrec.pad0 = hrec.pad1 = 0;
   if (p < A.npairs) {
     const int i = A.pair_i[p], j = A.pair_j[p], img = A.pair_img[p];
-    if (i < old_nown)
-      for (int e = old_half_off[i]; e < old_half_off[i + 1]; e++)
-        if (old_pair_j[e] == j) { q = e; break; }
+    // amap (decomposed rebuild): the atoms were renumbered; stayers keep their relative order and a ghost only ever
+    // matches an old ghost, so a surviving pair keeps its orientation (oi < oj)
+    const int oi = amap ? amap[i] : i, oj = amap ? amap[j] : j;
+    if (oi >= 0 && oj >= 0 && oi < old_nown && oi < oj)
+      for (int e = old_half_off[oi]; e < old_half_off[oi + 1]; e++)
+        if (old_pair_j[e] == oj) { q = e; break; }
     if (q >= 0) {
       hrec = old_hot[q];
-      if (hrec.n0 < 0 || hrec.img != img || hrec.i != i || hrec.j != j) q = -1;
+      if (hrec.n0 < 0 || hrec.img != img || hrec.i != oi || hrec.j != oj) q = -1;
+      hrec.i = i; hrec.j = j;
     }
     if (q >= 0) ntot = hrec.n0 + hrec.n1;
     else fresh_list[atomicAdd(nfresh, 1)] = p;

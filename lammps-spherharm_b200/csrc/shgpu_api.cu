@@ -114,6 +114,12 @@ struct sh_ctx {
   DevBuf<unsigned short> cache_pool[2];
   DevBuf<int> old_half_off, old_pair_j, fresh_list;   // pair list before the last rebuild (remap), pairs new to the cache
   int old_nown = 0, cache_cur = 0;
+  // cache carry-over across a DECOMPOSED rebuild (atoms are renumbered, ghosts re-created): snapshot of the old atoms
+  DevBuf<double> old_c, old_cc0, old_cq0;
+  DevBuf<long long> old_tag;
+  DevBuf<int> ghost_hash, amap;      // hash of the old ghosts by tag; new atom -> old atom (or -1)
+  int old_n = 0, old_stride = 0, ghost_hash_size = 0;
+  bool carry = false;
   int64_t cache_remaps = 0, atoms_epoch = 0, cache_epoch = -1;   // epoch: bumped whenever the atom set / order changes
   DevBuf<unsigned long long> cache_count;
   long long cache_cap = 0;
@@ -255,8 +261,8 @@ int build_neighbors(sh_ctx *h) {
   if (ev_tick(h, 5)) return -2;
   // a live candidate cache over the SAME atoms (single rank, no set_atoms in between) survives the rebuild: keep the
   // old half list so that run_split_pipeline can carry the cache entries over to the new pairs
-  const bool keep_cache = h->cache_state == CACHE_VALID && h->list_valid && h->nghost == 0 && h->npairs > 0 && h->atoms_epoch == h->cache_epoch;
-  if (keep_cache) {
+  const bool keep_cache = h->carry || (h->cache_state == CACHE_VALID && h->list_valid && h->nghost == 0 && h->npairs > 0 && h->atoms_epoch == h->cache_epoch);
+  if (keep_cache && !h->carry) {
     try { h->old_half_off.ensure((size_t)nown + 2); h->old_pair_j.ensure((size_t)h->npairs + 1); } catch (std::string &e) { return fail(h, e); }
     CU(cudaMemcpyAsync(h->old_half_off.p, h->half_off.p, ((size_t)nown + 1) * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
     CU(cudaMemcpyAsync(h->old_pair_j.p, h->pair_j.p, (size_t)h->npairs * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
@@ -350,6 +356,7 @@ int build_neighbors(sh_ctx *h) {
   h->list_valid = true; h->steps_since_build = 0; h->neighbor_builds++;
   // the pair list changed: a live cache over the same atoms is remapped, anything else is rebuilt
   h->cache_state = keep_cache ? CACHE_REMAP : CACHE_INVALID;
+  if (!keep_cache) h->carry = false;
   return 0;
 }
 
@@ -505,6 +512,17 @@ int run_split_pipeline(sh_ctx *h, PairArgs &P) {
       const int nxt = 1 - cur;
       try { h->cache_hot[nxt].ensure((size_t)np + 2); h->cache_pool[nxt].ensure((size_t)h->cache_cap + 64); }
       catch (std::string &e) { return fail(h, e); }
+      const int *amap = nullptr;
+      if (h->carry) {   // decomposed rebuild: find every new atom among the old ones, carry its cache reference state over
+        try { h->amap.ensure((size_t)h->n + 2); } catch (std::string &e) { return fail(h, e); }
+        const int nstay = h->dd.last_nstay, nown = (int)(h->n - h->nghost);
+        dd_cache_map_kernel<<<cdiv(h->n, 256), 256, 0, h->stream>>>(view_all(h), h->d_tag.p, nown, nstay, h->dd.order.p, h->old_tag.p, h->old_c.p,
+                                                                    h->old_stride, h->old_nown, h->old_n, h->ghost_hash.p, h->ghost_hash_size,
+                                                                    0.25 * h->dd.G.rc * h->dd.G.rc, h->old_cc0.p, h->old_cq0.p, h->amap.p);
+        h->kernel_launches++;
+        amap = h->amap.p;
+        h->carry = false; h->cache_epoch = h->atoms_epoch;
+      }
       if ((rc = check_validity())) return rc;
       if (tick(4)) return -2;
       CU(cudaMemsetAsync(h->cache_count.p, 0, 2 * sizeof(unsigned long long), h->stream));
@@ -512,7 +530,7 @@ int run_split_pipeline(sh_ctx *h, PairArgs &P) {
       C.pool = h->cache_pool[nxt].p; C.hot = h->cache_hot[nxt].p; C.count = h->cache_count.p;
       C.cap = h->cache_cap; C.overflow = h->split_flags.p + 2; C.level = h->cache_level + 1;
       cache_remap_kernel<<<cdiv(np, 256), 256, 0, h->stream>>>(P, h->old_half_off.p, h->old_pair_j.p, h->old_nown, h->cache_hot[cur].p,
-                                                                h->cache_pool[cur].p, C, h->fresh_list.p, h->split_flags.p + 3);
+                                                                h->cache_pool[cur].p, C, h->fresh_list.p, h->split_flags.p + 3, amap);
       pair_cache_build_kernel<4><<<std::max(1, std::min(cdiv(np, 4), h->sm_count * 8)), 4 * 32, 0, h->stream>>>(P, C, h->fresh_list.p, h->split_flags.p + 3);
       tock();
       h->kernel_launches += 2;
@@ -663,6 +681,7 @@ int compute_forces_device(sh_ctx *h) {
   h->kernel_launches++;
   CU(cudaGetLastError());
   h->forces_valid = true;
+  h->carry = false;   // a snapshot that this pair phase did not consume is stale from here on
   return 0;
 }
 
@@ -792,6 +811,7 @@ int sh_destroy(sh_ctx *h) {
   h->pool.release(); h->pool_flag.release(); h->pool_base.release(); h->pool_cap.release(); h->split_sc.release(); h->eval_plan.release(); h->slow_list.release();
   h->pd.release(); h->big_list.release(); h->split_flags.release();
   for (int k = 0; k < 2; k++) { h->cache_hot[k].release(); h->cache_pool[k].release(); }
+  h->old_c.release(); h->old_cc0.release(); h->old_cq0.release(); h->old_tag.release(); h->ghost_hash.release(); h->amap.release();
   h->old_half_off.release(); h->old_pair_j.release(); h->fresh_list.release(); h->cache_count.release(); h->cc0.release(); h->cq0.release(); h->drift.release();
   if (h->h_pool_count) { cudaFreeHost(h->h_pool_count); cudaFreeHost(h->h_split_sc); cudaFreeHost(h->h_cache_invalid); cudaEventDestroy(h->ev_sc); }
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
@@ -1037,6 +1057,29 @@ int step_finish(sh_ctx *h, int rebuild) {
   return 0;
 }
 
+// before a decomposed rebuild renumbers the atoms: keep what the candidate cache needs to survive it (old tags and
+// origins to recognise the atoms, the cache's reference state, the old pair list, a hash of the old ghosts by tag)
+int cache_snapshot(sh_ctx *h) {
+  const int n = (int)h->n, nown = (int)(h->n - h->nghost), st = h->stride, ng = (int)h->nghost;
+  int hs = 64;
+  while (hs < 2 * ng + 2) hs <<= 1;
+  try {
+    h->old_c.ensure(3 * (size_t)st); h->old_cc0.ensure(3 * (size_t)st); h->old_cq0.ensure(4 * (size_t)st); h->old_tag.ensure((size_t)n + 2);
+    h->old_half_off.ensure((size_t)nown + 2); h->old_pair_j.ensure((size_t)h->npairs + 1); h->ghost_hash.ensure(hs);
+  } catch (std::string &e) { return fail(h, e); }
+  CU(cudaMemcpyAsync(h->old_c.p, h->c.p, 3 * (size_t)st * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->old_cc0.p, h->cc0.p, 3 * (size_t)st * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->old_cq0.p, h->cq0.p, 4 * (size_t)st * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->old_tag.p, h->d_tag.p, (size_t)n * sizeof(long long), cudaMemcpyDeviceToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->old_half_off.p, h->half_off.p, ((size_t)nown + 1) * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->old_pair_j.p, h->pair_j.p, (size_t)h->npairs * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+  CU(cudaMemsetAsync(h->ghost_hash.p, 0xff, (size_t)hs * sizeof(int), h->stream));
+  if (ng > 0) { dd_ghost_hash_kernel<<<cdiv(ng, 256), 256, 0, h->stream>>>(h->old_tag.p, nown, ng, h->ghost_hash.p, hs); h->kernel_launches++; }
+  h->old_n = n; h->old_nown = nown; h->old_stride = st; h->ghost_hash_size = hs;
+  h->carry = true;
+  return 0;
+}
+
 // One full timestep of sh_run.  With the lagged neighbor decision (default) the host never waits for the step it is
 // enqueuing: whether step s rebuilds was predicted by the integrator of step s-1 (sc[5]) and arrives through a pinned
 // slot + event; a misprediction is counted (sc[6]) and reported as an error by sh_run.
@@ -1071,7 +1114,15 @@ int step_once(sh_ctx *h) {
     }
     CU(cudaMemsetAsync(h->scalars.p + 5, 0, sizeof(int), h->stream));
   }
-  if (dd) { if ((rc = rebuild ? dd_rebuild(h) : dd_forward(h))) return rc; }
+  if (dd && rebuild) {
+    h->carry = false;
+    const bool split = !(h->tune_variant & (1 | 2 | 4 | 8 | 32)) && ((h->tune_variant & 16) || h->npairs >= 16384);
+    if (split && h->cache_state == CACHE_VALID && h->list_valid && h->npairs > 0 && h->atoms_epoch == h->cache_epoch &&
+        h->cache_level + 1 < SH_CACHE_LEVELS) { if ((rc = cache_snapshot(h))) return rc; }
+    const bool carry = h->carry;
+    if ((rc = dd_rebuild(h))) return rc;
+    h->carry = carry;
+  } else if (dd) { if ((rc = dd_forward(h))) return rc; }
   return step_finish(h, rebuild);
 }
 }  // namespace

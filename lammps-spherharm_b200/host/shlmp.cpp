@@ -12,7 +12,12 @@
 // vx vy vz ; velocity <id> set ... ; pair_style spherharm ; pair_coeff i j k exponent ; fix <id> <grp>
 // nve/sh | wall/spherharm <xplane|yplane|zplane> <pos> <k> <exponent> [hi] | gravity <g> vector x y z |
 // viscous <gamma> ; neighbor <skin> bin ; neigh_modify every N [check yes|no] ; timestep ; thermo N ;
-// dump <id> <grp> custom N <file> ... ; run N ; write_restart <file> ; read_restart <file> ; print "..."
+// dump <id> <grp> custom N <file> ... ; run N ; write_restart <file> ; read_restart <file> ; print "..." ;
+// fix <id> <grp> deform N xy erate <rate> remap v   (Lees-Edwards shear: flow x, gradient y)
+//
+// shlmp -gpus N: N ranks = N threads of this process, one GPU each, every rank interprets the script (as MPI ranks do in
+// LAMMPS); the domain decomposition, ghost exchange and migration run inside libshgpu (sh_dd_*, NCCL); rank 0 prints
+// thermo output and writes the dumps from the state gathered over the ranks.
 //
 // Shape file: text rows `l m a_lm b_lm` (real orthonormal SH, no Condon-Shortley phase; missing rows = 0).
 // Data file: LAMMPS-style header (`N atoms`, `T atom types`, `xlo xhi` ...) and an `Atoms` section with
@@ -22,8 +27,14 @@
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <algorithm>
+#include <condition_variable>
 #include <map>
+#include <mutex>
+#include <numeric>
 #include <random>
+#include <thread>
+#include <unordered_map>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -84,6 +95,23 @@ void read_shape_file(const std::string &fn, int lmax, std::vector<double> &a, st
 
 struct Dump { std::string file; int every = 0; };
 
+// the ranks of one shlmp job (threads): a reusable barrier and per-rank slots for gathers / reductions
+struct Team {
+  int n = 1;
+  char uid[128] = {0};
+  std::mutex m; std::condition_variable cv; int waiting = 0; long generation = 0;
+  bool failed = false;
+  struct Part { std::vector<int64_t> tag; std::vector<double> x, v, quat; double e[3] = {0, 0, 0}; };
+  std::vector<Part> part;
+  void barrier() {
+    std::unique_lock<std::mutex> lk(m);
+    const long g = generation;
+    if (++waiting == n) { waiting = 0; generation++; cv.notify_all(); }
+    else cv.wait(lk, [&] { return generation != g || failed; });
+  }
+  void abort() { std::lock_guard<std::mutex> lk(m); failed = true; cv.notify_all(); }
+};
+
 struct Shlmp {
   sh_ctx *h = nullptr;
   bool dry = false;     // -check: parse and validate the script (files, arguments, command order) without a device
@@ -101,8 +129,16 @@ struct Shlmp {
   int64_t step = 0;
   std::vector<Dump> dumps;
   std::string restart_file;
+  int rank = 0, nranks = 1;
+  Team *team = nullptr;
+  double shear_rate = 0.0;
+  bool decomposed = false;           // the device order of the atoms is the library's, not the script's: go by tag
+  std::unordered_map<int64_t, int> type_of_tag;
+  // this rank's owned atoms as last pulled from the device
+  std::vector<int64_t> ltag; std::vector<double> lx, lv, lq;
 
   void ck(int rc) { if (rc != 0) error_all(FLERR, sh_last_error(h)); }
+  bool master() const { return rank == 0; }
 
   // Pair::init_style + AtomVec upload + fixes' init
   void init() {
@@ -119,7 +155,10 @@ struct Shlmp {
     }
     if (!restart_file.empty() && avec.nlocal() > 0) error_all(FLERR, "read_restart cannot be combined with create_atoms / read_data");
     if (!pair_defined) error_all(FLERR, "pair_style spherharm is required");
+    if (nranks > 1) { ck(sh_dd_init(h, rank, nranks, team->uid, nullptr)); decomposed = true; }
     ck(sh_set_box(h, lo, hi, periodic));
+    if (shear_rate != 0.0) { ck(sh_set_shear(h, shear_rate)); decomposed = true; }
+    if (decomposed && !restart_file.empty()) error_all(FLERR, "read_restart is not supported with -gpus > 1 or fix deform");
     ck(sh_set_quadrature(h, avec.n_theta, avec.n_phi));
     for (size_t s = 0; s < avec.shape_files.size(); s++) {
       std::vector<double> a, b;
@@ -148,23 +187,59 @@ struct Shlmp {
     ck(sh_set_damping(h, gamma, gamma));
     ck(sh_set_neighbor(h, skin, every, check));
     ck(sh_set_timestep(h, dt));
+    for (size_t i = 0; i < avec.nlocal(); i++) type_of_tag[avec.tag[i]] = avec.type[i];
     initialised = true;
   }
-  void pull_state() {   // device -> host staging (dump / thermo / later `set` commands)
-    const int64_t n = (int64_t)avec.nlocal();
-    if (n) ck(sh_get_atoms(h, n, avec.x.data(), avec.v.data(), avec.quat.data(), avec.angmom.data(), nullptr, nullptr));
+  // device -> host staging (dump / thermo).  Decomposed runs: every rank pulls its owned atoms, rank 0 merges them by tag
+  // into the script-order arrays of avec.
+  void pull_state() {
+    if (!decomposed) {
+      const int64_t n = (int64_t)avec.nlocal();
+      if (n) ck(sh_get_atoms(h, n, avec.x.data(), avec.v.data(), avec.quat.data(), avec.angmom.data(), nullptr, nullptr));
+      return;
+    }
+    int64_t nl = 0, ng = 0;
+    ck(sh_dd_get_info(h, nullptr, nullptr, &nl, &ng, nullptr, nullptr));
+    const int64_t nall = nl + ng;
+    std::vector<int64_t> tg(nall); std::vector<double> x(3 * nall), v(3 * nall), q(4 * nall);
+    if (nall) { ck(sh_get_tags(h, nall, tg.data())); ck(sh_get_atoms(h, nall, x.data(), v.data(), q.data(), nullptr, nullptr, nullptr)); }
+    Team::Part mine;
+    mine.tag.assign(tg.begin(), tg.begin() + nl); mine.x.assign(x.begin(), x.begin() + 3 * nl); mine.v.assign(v.begin(), v.begin() + 3 * nl);
+    mine.quat.assign(q.begin(), q.begin() + 4 * nl);
+    if (team) { team->part[rank] = std::move(mine); team->barrier(); }
+    if (master()) {
+      std::unordered_map<int64_t, size_t> where;
+      for (size_t i = 0; i < avec.nlocal(); i++) where[avec.tag[i]] = i;
+      auto merge = [&](const Team::Part &p) {
+        for (size_t k = 0; k < p.tag.size(); k++) {
+          const size_t i = where.at(p.tag[k]);
+          for (int d = 0; d < 3; d++) { avec.x[3 * i + d] = p.x[3 * k + d]; avec.v[3 * i + d] = p.v[3 * k + d]; }
+          for (int d = 0; d < 4; d++) avec.quat[4 * i + d] = p.quat[4 * k + d];
+        }
+      };
+      if (team) for (auto &p : team->part) merge(p); else merge(mine);
+    }
+    if (team) team->barrier();
   }
   void write_thermo(bool header) {
-    double kt, kr, ec;
-    ck(sh_get_energy(h, &kt, &kr, &ec));
+    double e[3];
+    ck(sh_get_energy(h, &e[0], &e[1], &e[2]));
+    if (team) {
+      for (int d = 0; d < 3; d++) team->part[rank].e[d] = e[d];
+      team->barrier();
+      if (master()) for (int r = 1; r < nranks; r++) for (int d = 0; d < 3; d++) e[d] += team->part[r].e[d];
+      team->barrier();
+    }
+    if (!master()) return;
     if (header) printf("%10s %16s %16s %16s %16s\n", "Step", "KinEng", "RotKinEng", "E_contact", "TotEng");
-    printf("%10lld %16.9g %16.9g %16.9g %16.9g\n", (long long)step, kt, kr, ec, kt + kr + ec);
+    printf("%10lld %16.9g %16.9g %16.9g %16.9g\n", (long long)step, e[0], e[1], e[2], e[0] + e[1] + e[2]);
     fflush(stdout);
   }
   void write_dumps(bool force) {
     for (auto &d : dumps) {
       if (!force && (d.every <= 0 || step % d.every)) continue;
       pull_state();
+      if (!master()) continue;
       FILE *f = fopen(d.file.c_str(), step == 0 || force ? (step == 0 ? "w" : "a") : "a");
       if (!f) error_all(FLERR, "Cannot open dump file " + d.file);
       fprintf(f, "ITEM: TIMESTEP\n%lld\nITEM: NUMBER OF ATOMS\n%zu\nITEM: BOX BOUNDS\n", (long long)step, avec.nlocal());
@@ -178,8 +253,8 @@ struct Shlmp {
     }
   }
   void run(int64_t nsteps) {
-    if (dry) { init(); printf("check: run %lld with %zu atoms, %zu shape(s), %zu wall(s) OK\n", (long long)nsteps, avec.nlocal(), avec.shape_files.size(), walls.size()); step += nsteps; return; }
-    if (!nve_defined) fprintf(stderr, "WARNING: no fix nve/sh defined; atoms are integrated by the device step anyway\n");
+    if (dry) { init(); if (shear_rate != 0.0 && !(periodic[0] && periodic[1])) error_all(FLERR, "fix deform xy needs a box periodic in x and y"); printf("check: run %lld with %zu atoms, %zu shape(s), %zu wall(s) OK\n", (long long)nsteps, avec.nlocal(), avec.shape_files.size(), walls.size()); step += nsteps; return; }
+    if (!nve_defined && master()) fprintf(stderr, "WARNING: no fix nve/sh defined; atoms are integrated by the device step anyway\n");
     init();
     ck(sh_compute_forces(h));
     write_thermo(true);
@@ -200,8 +275,8 @@ struct Shlmp {
     double sp, sn, so; int64_t pl;
     ck(sh_get_timers(h, &sp, &pl, &sn, &so));
     double rl, rt; ck(sh_get_run_time(h, &rl, &rt));
-    printf("Loop time of %g on 1 GPU for %lld steps with %zu atoms\n", rt, (long long)nsteps, avec.nlocal());
-    printf("Pair  time (device) %g s in %lld launches | Neigh %g s in %lld builds | pair evals %lld | nodes evaluated %lld inside %lld\n",
+    if (master()) printf("Loop time of %g on %d GPU%s for %lld steps with %zu atoms\n", rt, nranks, nranks > 1 ? "s" : "", (long long)nsteps, avec.nlocal());
+    if (master()) printf("Pair  time (device) %g s in %lld launches | Neigh %g s in %lld builds | pair evals %lld | nodes evaluated %lld inside %lld\n",
            sp, (long long)pl, sn, (long long)nb, (long long)pe, (long long)ne, (long long)ni);
     pull_state();
   }
@@ -312,6 +387,13 @@ void execute(Shlmp &S, const std::vector<std::string> &t) {
     }
     if (style == "gravity") { need(9); if (t[5] != "vector") error_all(FLERR, "Only fix gravity <g> vector x y z is supported"); const double gm = std::stod(t[4]); double v[3] = {std::stod(t[6]), std::stod(t[7]), std::stod(t[8])}; const double nn = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); for (int d = 0; d < 3; d++) S.g[d] = gm * v[d] / nn; return; }
     if (style == "viscous") { need(5); S.gamma = std::stod(t[4]); return; }
+    if (style == "deform") {   // fix ID group deform N xy erate R [remap v]: Lees-Edwards shear at engineering rate R
+      need(8);
+      if (t[5] != "xy" || t[6] != "erate") error_all(FLERR, "Only fix deform N xy erate <rate> remap v is supported");
+      if (S.initialised) error_all(FLERR, "fix deform after the first run is not supported");
+      S.shear_rate = std::stod(t[7]);
+      return;
+    }
     error_all(FLERR, "Unknown fix style " + style);
   }
   if (c == "neighbor") { need(2); S.skin = std::stod(t[1]); return; }
@@ -320,37 +402,35 @@ void execute(Shlmp &S, const std::vector<std::string> &t) {
   if (c == "thermo") { need(2); S.thermo = std::stoi(t[1]); return; }
   if (c == "dump") { need(6); Dump d; d.every = std::stoi(t[4]); d.file = t[5]; S.dumps.push_back(d); return; }
   if (c == "run") { need(2); S.run(std::stoll(t[1])); return; }
-  if (c == "write_restart") { need(2); S.init(); if (!S.dry) S.ck(sh_write_snapshot(S.h, t[1].c_str(), S.step)); return; }
+  if (c == "write_restart") {
+    need(2); S.init();
+    if (S.decomposed) error_all(FLERR, "write_restart is not supported with -gpus > 1 or fix deform");
+    if (!S.dry) S.ck(sh_write_snapshot(S.h, t[1].c_str(), S.step));
+    return;
+  }
   if (c == "read_restart") {   // atoms + box from a snapshot; atom_style (shapes) must already be defined
     need(2);
     if (S.avec.lmax < 0) error_all(FLERR, "atom_style spherharm must be defined before read_restart");
     S.restart_file = t[1]; S.box_defined = true;
     return;
   }
-  if (c == "print") { need(2); printf("%s\n", t[1].c_str()); return; }
+  if (c == "print") { need(2); if (S.master()) printf("%s\n", t[1].c_str()); return; }
   error_all(FLERR, "Unknown command: " + c);
 }
 
-}  // namespace
-
-int main(int argc, char **argv) {
-  std::string infile; int device = 0; bool check_only = false;
-  for (int k = 1; k < argc; k++) {
-    std::string a = argv[k];
-    if ((a == "-in" || a == "-i") && k + 1 < argc) infile = argv[++k];
-    else if (a == "-device" && k + 1 < argc) device = std::atoi(argv[++k]);
-    else if (a == "-check") check_only = true;
-    else if (a == "-h" || a == "--help") { printf("usage: shlmp -in <input script> [-device N] [-check]\n"); return 0; }
-  }
+// one rank: interpret the whole script on its own handle / device
+int run_rank(int rank, int nranks, int device, Team *team, const std::vector<std::string> &lines, bool check_only) {
   Shlmp S;
-  S.dry = check_only;
+  S.dry = check_only; S.rank = rank; S.nranks = nranks; S.team = team;
   try {
-    if (!check_only && sh_create(&S.h, device) != 0) { fprintf(stderr, "ERROR: no usable CUDA device (libshgpu has no CPU fallback)\n"); return 1; }
-    std::ifstream fin; std::istream *in = &std::cin;
-    if (!infile.empty()) { fin.open(infile); if (!fin) { fprintf(stderr, "ERROR: Cannot open input script %s\n", infile.c_str()); return 1; } in = &fin; }
-    printf("shlmp (SPHERHARM on libshgpu %d)\n", sh_version());
-    std::string line, acc;
-    while (std::getline(*in, line)) {
+    if (!check_only && sh_create(&S.h, device) != 0) {
+      fprintf(stderr, "ERROR: no usable CUDA device %d (libshgpu has no CPU fallback)\n", device);
+      if (team) team->abort();
+      return 1;
+    }
+    if (rank == 0) printf("shlmp (SPHERHARM on libshgpu %d)%s\n", sh_version(), nranks > 1 ? ", decomposed over several GPUs" : "");
+    std::string acc;
+    for (const std::string &line : lines) {
       if (!line.empty() && line.back() == '&') { acc += line.substr(0, line.size() - 1); continue; }
       acc += line;
       auto t = tokenize(acc); acc.clear();
@@ -359,13 +439,43 @@ int main(int argc, char **argv) {
     }
   } catch (Err &e) {
     fprintf(stderr, "%s\n", e.msg.c_str());
+    if (team) team->abort();
     if (S.h) sh_destroy(S.h);
     return 1;
   } catch (std::exception &e) {
     fprintf(stderr, "ERROR: %s\n", e.what());
+    if (team) team->abort();
     if (S.h) sh_destroy(S.h);
     return 1;
   }
   if (S.h) sh_destroy(S.h);
   return 0;
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+  std::string infile; int device = 0, ngpus = 1; bool check_only = false;
+  for (int k = 1; k < argc; k++) {
+    std::string a = argv[k];
+    if ((a == "-in" || a == "-i") && k + 1 < argc) infile = argv[++k];
+    else if (a == "-device" && k + 1 < argc) device = std::atoi(argv[++k]);
+    else if (a == "-gpus" && k + 1 < argc) ngpus = std::atoi(argv[++k]);
+    else if (a == "-check") check_only = true;
+    else if (a == "-h" || a == "--help") { printf("usage: shlmp -in <input script> [-device N] [-gpus N] [-check]\n"); return 0; }
+  }
+  if (ngpus < 1 || ngpus > 64) { fprintf(stderr, "ERROR: -gpus must be 1..64\n"); return 1; }
+  std::ifstream fin; std::istream *in = &std::cin;
+  if (!infile.empty()) { fin.open(infile); if (!fin) { fprintf(stderr, "ERROR: Cannot open input script %s\n", infile.c_str()); return 1; } in = &fin; }
+  std::vector<std::string> lines;
+  for (std::string line; std::getline(*in, line);) lines.push_back(line);
+  if (ngpus == 1 || check_only) return run_rank(0, 1, device, nullptr, lines, check_only);
+  Team team;
+  team.n = ngpus; team.part.resize(ngpus);
+  if (sh_dd_unique_id(team.uid, (int)sizeof team.uid) != 0) { fprintf(stderr, "ERROR: NCCL is not available (libnccl.so.2)\n"); return 1; }
+  std::vector<int> rc(ngpus, 0);
+  std::vector<std::thread> th;
+  for (int r = 0; r < ngpus; r++) th.emplace_back([&, r] { rc[r] = run_rank(r, ngpus, device + r, &team, lines, false); });
+  for (auto &t : th) t.join();
+  return *std::max_element(rc.begin(), rc.end());
 }

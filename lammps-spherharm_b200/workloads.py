@@ -171,6 +171,19 @@ def packing(ncell, lmax, grid, nshapes=8, seed=30, nn_frac=1.9, periodic=True, k
                 gravity=(0, 0, 0), skin=skin, dt=dt)
 
 
+def shear_box(cfg, rate):
+    """configs[3] style: turn a periodic packing into a Lees-Edwards shear box (flow x, gradient y) with the linear
+    velocity profile v_x = rate * (y - y_mid) on top of its velocities."""
+    cfg = dict(cfg)
+    lo, hi, _ = cfg["box"]
+    v = np.array(cfg["v"], dtype=float, copy=True)
+    v[:, 0] += rate * (np.asarray(cfg["x"])[:, 1] - 0.5 * (lo[1] + hi[1]))
+    cfg["v"] = v
+    cfg["shear"] = float(rate)
+    cfg["name"] = cfg["name"] + "_shear"
+    return cfg
+
+
 def config3_packing(n_target=100000, lmax=30, grid=(48, 96), seed=30):
     """configs[2]: ~100k polydisperse-shape packing, 8 SH shape types, l_max=30."""
     m = max(2, int(round((n_target / 4.0) ** (1.0 / 3.0))))
@@ -204,6 +217,8 @@ def apply(sim, cfg):
     """Drive a sim object (sh_* call surface) with a config dict."""
     if cfg["box"] is not None:
         sim.set_box(*cfg["box"])
+    if cfg.get("shear"):
+        sim.set_shear(cfg["shear"])          # Lees-Edwards: flow x, gradient y (before the atoms are created)
     sim.set_quadrature(*cfg["grid"])
     ids = [sim.add_shape(cfg["lmax"], a, b, cfg["density"]) for (a, b) in cfg["shapes"]]
     sim.set_atoms(cfg["shape_id"], cfg["x"], cfg["v"], cfg["quat"], cfg["angmom"])

@@ -120,6 +120,9 @@ class Oracle:
     def set_damping(self, gamma_lin, gamma_rot):
         self._ck(self.L.orc_set_damping(self.h, C.c_double(gamma_lin), C.c_double(gamma_rot)))
 
+    def set_shear(self, rate):
+        self._ck(self.L.orc_set_shear(self.h, C.c_double(rate)))
+
     def set_timestep(self, dt):
         self._ck(self.L.orc_set_timestep(self.h, C.c_double(dt)))
 

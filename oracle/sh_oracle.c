@@ -57,6 +57,7 @@ struct orc_ctx {
   int64_t npair, cappair; pairres_t *pr;
   int64_t cnt_pairs, cnt_trans, cnt_eval, cnt_inside;
   double e_contact; int forces_valid;
+  double shear_rate, time;           /* Lees-Edwards shear (flow x, gradient y): image offset = shear_rate * Ly * time */
 };
 
 static int fail(orc_ctx *c, const char *msg) { snprintf(c->err, sizeof c->err, "%s", msg); return -1; }
@@ -396,6 +397,11 @@ int orc_set_gravity(orc_ctx *c, const double g[3]) { for (int d = 0; d < 3; d++)
 int orc_set_neighbor(orc_ctx *c, double skin, int every, int check) { (void)every; (void)check; if (skin < 0) return fail(c, "skin < 0"); c->skin = skin; return 0; }
 int orc_set_timestep(orc_ctx *c, double dt) { if (!(dt > 0)) return fail(c, "dt <= 0"); c->dt = dt; return 0; }
 int orc_set_damping(orc_ctx *c, double gl, double gr) { if (gl < 0 || gr < 0) return fail(c, "damping < 0"); c->gamma_lin = gl; c->gamma_rot = gr; return 0; }
+int orc_set_shear(orc_ctx *c, double rate) {
+  if (rate != 0.0 && !(c->periodic[0] && c->periodic[1])) return fail(c, "shear needs a box periodic in x and y");
+  c->shear_rate = rate; c->time = 0.0; c->forces_valid = 0;
+  return 0;
+}
 int orc_set_threads(orc_ctx *c, int nthreads) { c->nthreads = nthreads > 0 ? nthreads : 1; return 0; }
 
 /* ---------------- pose: Rs = R(q) Rp^T, c = x - Rs com ---------------- */
@@ -423,6 +429,17 @@ static void compute_pose(orc_ctx *c) {
 
 /* ---------------- neighbor list (A.8): unordered pairs i<j, bounding spheres + skin ---------------- */
 static void min_image(const orc_ctx *c, double d[3]) {
+  if (c->shear_rate != 0.0) {
+    /* Lees-Edwards: the image cell n_y boxes up is displaced by n_y * offset(t) along x (SURVEY §8d cfg 4).  Coordinates
+       are never wrapped here, so the offset is simply rate * Ly * t. */
+    const double Lx = c->hi[0] - c->lo[0], Ly = c->hi[1] - c->lo[1], off = c->shear_rate * Ly * c->time;
+    const double ny = rint(d[1] / Ly);
+    d[1] = d[1] - Ly * ny;
+    d[0] = d[0] - ny * off;
+    d[0] = d[0] - Lx * rint(d[0] / Lx);
+    if (c->periodic[2]) { double Lz = c->hi[2] - c->lo[2]; d[2] = d[2] - Lz * rint(d[2] / Lz); }
+    return;
+  }
   for (int k = 0; k < 3; k++)
     if (c->periodic[k]) { double Lk = c->hi[k] - c->lo[k]; d[k] = d[k] - Lk * rint(d[k] / Lk); }
 }
@@ -482,7 +499,11 @@ static int build_neighbors(orc_ctx *c) {
       else if (c->periodic[k]) { lo3[k] = cell[3 * i + k] - 1; hi3[k] = cell[3 * i + k] + 1; }
       else { lo3[k] = cell[3 * i + k] > 0 ? cell[3 * i + k] - 1 : 0; hi3[k] = cell[3 * i + k] < nc[k] - 1 ? cell[3 * i + k] + 1 : nc[k] - 1; }
     }
-    for (int cz = lo3[2]; cz <= hi3[2]; cz++) for (int cy = lo3[1]; cy <= hi3[1]; cy++) for (int cx = lo3[0]; cx <= hi3[0]; cx++) {
+    for (int cz = lo3[2]; cz <= hi3[2]; cz++) for (int cy = lo3[1]; cy <= hi3[1]; cy++) {
+      /* under shear the row across the y boundary is displaced along x by an arbitrary amount: scan the whole row */
+      const int sheared_row = c->shear_rate != 0.0 && (cy < 0 || cy >= nc[1]) && nc[0] > 1;
+      const int x0 = sheared_row ? 0 : lo3[0], x1 = sheared_row ? nc[0] - 1 : hi3[0];
+      for (int cx = x0; cx <= x1; cx++) {
       int wx = (cx % nc[0] + nc[0]) % nc[0], wy = (cy % nc[1] + nc[1]) % nc[1], wz = (cz % nc[2] + nc[2]) % nc[2];
       int64_t id = ((int64_t)wz * nc[1] + wy) * nc[0] + wx;
       for (int j = head[id]; j >= 0; j = next[j]) {
@@ -492,6 +513,7 @@ static int build_neighbors(orc_ctx *c) {
         double rc = c->shp[c->shape[i]].rmax + c->shp[c->shape[j]].rmax + c->skin;
         if (i >= c->n - c->nghost) continue;
         if (d[0] * d[0] + d[1] * d[1] + d[2] * d[2] < rc * rc) push_pair(c, (int)i, j);
+      }
       }
     }
   }
@@ -700,6 +722,7 @@ int orc_run(orc_ctx *c, int64_t nsteps) {
       }
       richardson(&c->q[4 * i], &c->L[3 * i], s->inertia, dth);
     }
+    c->time += dt;
     if (orc_compute_forces(c)) return -1;
 #pragma omp parallel for num_threads(c->nthreads)
     for (int64_t i = 0; i < c->n; i++) {

@@ -42,6 +42,8 @@ int orc_set_gravity(orc_ctx *c, const double g[3]);
 int orc_set_neighbor(orc_ctx *c, double skin, int every, int check);
 int orc_set_timestep(orc_ctx *c, double dt);
 int orc_set_damping(orc_ctx *c, double gamma_lin, double gamma_rot);
+/* Lees-Edwards shear: flow along x, gradient along y, rate = dvx/dy; after orc_set_box */
+int orc_set_shear(orc_ctx *c, double rate);
 int orc_set_threads(orc_ctx *c, int nthreads);
 int orc_compute_forces(orc_ctx *c);
 int orc_run(orc_ctx *c, int64_t nsteps);

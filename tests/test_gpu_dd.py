@@ -21,7 +21,9 @@ pytestmark = pytest.mark.gpu
 
 
 def _cfg():
-    return W.packing((6, 4, 4), 20, (32, 64), nshapes=4, seed=21, periodic=True, name="dd", skin=0.03, vel_sigma=0.5, dt=4e-4)
+    cfg = W.packing((6, 4, 4), 20, (32, 64), nshapes=4, seed=21, periodic=True, name="dd", skin=0.03, vel_sigma=0.5, dt=4e-4)
+    cfg["v"] = cfg["v"] + np.array([2.0, 1.0, 0.0])      # a drift, so that atoms cross brick / box boundaries (migration)
+    return cfg
 
 
 def _sorted_owned(sim):
@@ -51,6 +53,9 @@ def test_self_ghost_decomposition_equals_periodic_engine(variant, sync):
     ref.run(nsteps); dd.run(nsteps)
     r1 = ref.get_atoms(); d1, info = _sorted_owned(dd)
     assert info["border_builds"] >= 3, info          # rebuilds (migration + borders) happened
+    if variant == 16:                                # the candidate cache survived them (carried over by tag)
+        cs = dd.get_cache_stats()
+        assert cs["cache_remaps"] >= 2, cs
     L = np.asarray(cfg["box"][1]) - np.asarray(cfg["box"][0])
     dx = d1["x"] - r1["x"]; dx -= L * np.rint(dx / L)
     assert np.abs(dx).max() <= 1e-9, np.abs(dx).max()
@@ -86,6 +91,7 @@ local = int(os.environ["LOCAL_RANK"]); torch.cuda.set_device(local)
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 cfg = W.packing((6, 4, 4), 20, (32, 64), nshapes=4, seed=21, periodic=True, name="mr", skin=0.03, vel_sigma=0.5, dt=4e-4)
+cfg["v"] = cfg["v"] + np.array([2.0, 1.0, 0.0])      # a drift, so that atoms cross the brick boundaries (migration)
 nsteps = 300
 for variant in (16, 0):
     sim = D.native_engine(pkg, cfg, local)
@@ -128,3 +134,40 @@ def test_two_gpu_native_decomposition_equals_single_gpu(tmp_path):
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     print(out.read_text())
     assert out.read_text().startswith("ok")
+
+
+@pytest.mark.parametrize("variant", [0, 16])
+def test_lees_edwards_shear_box_vs_oracle(variant):
+    """BASELINE configs[3] physics at test size: periodic box sheared by Lees-Edwards images (sh_set_shear) against the
+    oracle's sheared minimum image, forces at several times and the trajectory in between."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as O
+    rate = 0.6
+    cfg = W.shear_box(W.packing((5, 4, 4), 20, (32, 64), nshapes=4, seed=33, periodic=True, name="le", skin=0.04, vel_sigma=0.3, dt=4e-4), rate)
+    lo, hi, _ = cfg["box"]
+    L = np.asarray(hi) - np.asarray(lo)
+    g = pkg.ShGpu(); W.apply(g, cfg); g.set_pair_tuning(0, 0, variant)
+    o = O.Oracle(threads=8); W.apply(o, cfg)
+    t = 0.0
+    for nsteps in (0, 120, 180):
+        if nsteps:
+            g.run(nsteps); o.run(nsteps); t += nsteps * cfg["dt"]
+        else:
+            g.compute_forces(); o.compute_forces()
+        gs, info = _sorted_owned(g)
+        os_ = o.get_atoms()
+        off, vs = rate * L[1] * t, rate * L[1]
+        ny = np.rint((os_["x"][:, 1] - gs["x"][:, 1]) / L[1])           # the oracle never wraps: it holds image +ny
+        dx = os_["x"] - gs["x"]
+        dx[:, 1] -= ny * L[1]; dx[:, 0] -= ny * off
+        dx[:, 0] -= L[0] * np.rint(dx[:, 0] / L[0]); dx[:, 2] -= L[2] * np.rint(dx[:, 2] / L[2])
+        assert np.abs(dx).max() <= 1e-8, (nsteps, np.abs(dx).max())
+        dv = os_["v"] - gs["v"]; dv[:, 0] -= ny * vs
+        assert np.abs(dv).max() <= 1e-7 * max(1.0, np.abs(os_["v"]).max()), (nsteps, np.abs(dv).max())
+        fs = max(np.abs(os_["f"]).max(), 1e-30)
+        assert fs > 1.0
+        assert np.abs(os_["f"] - gs["f"]).max() <= 1e-7 * fs, (nsteps, np.abs(os_["f"] - gs["f"]).max() / fs)
+        assert np.abs(os_["torque"] - gs["torque"]).max() <= 1e-7 * fs
+    assert info["nghost"] > 0 and info["border_builds"] >= 3
+    assert np.abs(ny).max() >= 1            # some atoms did cross the sheared boundary
+    g.close(); o.close()

@@ -169,3 +169,40 @@ def test_cell_list_equals_brute_force():
     have = set(zip(pairs["tag_i"].tolist(), pairs["tag_j"].tolist()))
     assert want <= have
     assert all((a in sub + 1 or b in sub + 1) is False or (a, b) in want for (a, b) in have if (a - 1) in sub or (b - 1) in sub)
+
+
+def test_lees_edwards_image_equals_explicit_placement():
+    """Lees-Edwards minimum image of the oracle: a pair that touches across the sheared y boundary feels exactly the
+    force of the same two particles placed side by side without any boundary."""
+    a, b = W.ellipsoid_shape(12)
+    rng = np.random.default_rng(5)
+    quat = W.random_quaternions(rng, 2)
+    L = np.array([12.0, 10.0, 9.0])
+    rate, t_steps, dt = 0.37, 25, 1e-3
+    off = rate * L[1] * t_steps * dt
+    xa = np.array([4.0, 9.3, 4.0])
+    x_img = xa + np.array([0.25, 1.3, 0.1])            # where B's image (one box up) must sit
+    xb = x_img - np.array([off, L[1], 0.0])             # B itself: one box down, displaced back by the offset
+    def run(x, box, shear):
+        o = O.Oracle()
+        if box is not None:
+            o.set_box(*box)
+        if shear:
+            o.set_shear(shear)
+        o.set_quadrature(24, 48)
+        sid = o.add_shape(12, a, b, 1.0)
+        o.set_atoms(np.zeros(2, np.int32), x, np.zeros((2, 3)), quat, np.zeros((2, 3)))
+        o.pair_coeff(sid, sid, 1e3, 1.0)
+        o.set_neighbor(0.1); o.set_timestep(dt)
+        return o
+    o1 = run(np.array([xa, xb]), (np.zeros(3), L, (1, 1, 1)), rate)
+    # frozen particles: advance the clock only (zero velocities, forces switched off by k = 0 during the clock steps)
+    o1.pair_coeff(0, 0, 0.0, 1.0); o1.run(t_steps); o1.pair_coeff(0, 0, 1e3, 1.0)
+    o1.compute_forces()
+    o2 = run(np.array([xa, x_img]), None, 0.0)
+    o2.compute_forces()
+    f1, f2 = o1.get_atoms()["f"], o2.get_atoms()["f"]
+    assert np.abs(f2).max() > 1.0                       # they do touch
+    assert np.abs(f1 - f2).max() <= 1e-10 * np.abs(f2).max()
+    t1, t2 = o1.get_atoms()["torque"], o2.get_atoms()["torque"]
+    assert np.abs(t1 - t2).max() <= 1e-10 * np.abs(f2).max()

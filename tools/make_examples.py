@@ -46,6 +46,9 @@ def main(outdir=os.path.join(ROOT, "examples")):
     hi = cfg["x"].max(0) + 3.0
     lo[2] = 0.0
     write_data(os.path.join(outdir, "data.wall_1000"), cfg, (lo, hi))
+    # BASELINE configs[3] at example size: periodic mono-shape packing sheared by Lees-Edwards images (in.shear_box)
+    cfg = W.shear_box(W.packing((5, 4, 4), 20, (32, 64), nshapes=1, seed=33, periodic=True, vel_sigma=0.3), 0.6)
+    write_data(os.path.join(outdir, "data.shear_320"), cfg, (cfg["box"][0], cfg["box"][1]))
 
 
 if __name__ == "__main__":
