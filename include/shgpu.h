@@ -47,6 +47,11 @@ int sh_set_atoms(sh_ctx *h, int64_t n, const int64_t *tag, const int *shape, con
 
 /* pair_style spherharm / pair_coeff i j k exponent  (Pair::settings, Pair::coeff) -------------- */
 int sh_pair_coeff(sh_ctx *h, int shape_i, int shape_j, double k, double exponent);
+/* dissipative contact terms (pair_coeff i j k exponent gamma_n gamma_t mu in shlmp; the reference's model is
+ * unknown — builder's choice, oracle A.5b): viscous normal damping gamma_n (the normal force never turns attractive) and
+ * tangential damping gamma_t capped by Coulomb friction mu |F_n|, both from the relative velocity at the overlap centroid,
+ * with the matching torques.  All zero (default) = the purely elastic volume contact. */
+int sh_pair_dissipation(sh_ctx *h, int shape_i, int shape_j, double gamma_n, double gamma_t, double mu);
 /* fix wall for SH particles (Fix::post_force): plane through point, normal into the domain -- */
 int sh_add_wall(sh_ctx *h, const double point[3], const double normal[3], double k,
                 double exponent);
@@ -119,6 +124,10 @@ int sh_get_atoms(const sh_ctx *h, int64_t n, double *x, double *v, double *quat,
 int sh_get_pairs(const sh_ctx *h, int64_t cap, int64_t *npairs, int64_t *tag_i, int64_t *tag_j,
                  double *V, double *F, double *tau_i, double *tau_j, double *centroid);
 int sh_get_energy(const sh_ctx *h, double *ke_trans, double *ke_rot, double *e_contact);
+/* compute pressure / stress (row-major 3x3 sums over this rank): kinetic = sum_i m v v over owned atoms, virial =
+ * sum_pairs (x_i - x_j) (x) F_i with pairs that involve a ghost counted half; pressure tensor = (kinetic + virial summed
+ * over the ranks) / box volume.  Wall forces are not included. */
+int sh_get_stress(const sh_ctx *h, double virial[9], double kinetic[9]);
 int sh_get_counters(const sh_ctx *h, int64_t *pair_evals, int64_t *nodes_transformed,
                     int64_t *nodes_evaluated, int64_t *nodes_inside, int64_t *neighbor_builds,
                     int64_t *kernel_launches);

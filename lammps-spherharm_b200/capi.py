@@ -121,6 +121,14 @@ class ShGpu:
     def pair_coeff(self, si, sj, k, exponent):
         self._ck(self.L.sh_pair_coeff(self.h, int(si), int(sj), C.c_double(k), C.c_double(exponent)))
 
+    def pair_dissipation(self, si, sj, gamma_n, gamma_t, mu):
+        self._ck(self.L.sh_pair_dissipation(self.h, int(si), int(sj), C.c_double(gamma_n), C.c_double(gamma_t), C.c_double(mu)))
+
+    def get_stress(self):
+        w, k = np.zeros(9), np.zeros(9)
+        self._ck(self.L.sh_get_stress(self.h, _p(w), _p(k)))
+        return dict(virial=w.reshape(3, 3), kinetic=k.reshape(3, 3))
+
     def add_wall(self, point, normal, k, exponent):
         p, nn = _d(point), _d(normal)
         self._ck(self.L.sh_add_wall(self.h, _p(p), _p(nn), C.c_double(k), C.c_double(exponent)))

@@ -197,4 +197,19 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// angular velocity in the space frame from the angular momentum: w = R(q) diag(1/I) R(q)^T L (q: principal -> space)
+__device__ __forceinline__ void omega_from_angmom(const double q[4], const double L[3], const double I[3],
+                                                  double w[3]) {
+  double R[9];
+  quat_to_mat(q, R);
+  double wb[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const double lb = R[k] * L[0] + R[3 + k] * L[1] + R[6 + k] * L[2];
+    wb[k] = (I[k] > 0) ? lb / I[k] : 0.0;
+  }
+#pragma unroll
+  for (int r = 0; r < 3; r++) w[r] = R[3 * r] * wb[0] + R[3 * r + 1] * wb[1] + R[3 * r + 2] * wb[2];
+}
+
 }  // namespace shgpu

@@ -45,6 +45,10 @@ struct PairArgs {
   int nlocal;                 // atoms >= nlocal are ghosts (counters[4] counts pairs with a ghost)
   const int *pair_list;       // optional indirection: process pairs pair_list[0..npairs) (deep-contact list)
   const int *npairs_dev;      // optional: number of pairs lives on the device (deep-contact list of the split pipeline)
+  // dissipative contact terms (oracle A.5b): viscous normal damping + Coulomb-capped tangential friction
+  int dissip;
+  const double *v, *L, *q;    // SoA velocities, angular momenta, quaternions (ghosts carry theirs when dissip is on)
+  const double *pgn, *pgt, *pmu;
 };
 
 // minimum-image separation d = c_i - c_j - L n with the image n stored at the neighbor build: the same value, bit for
@@ -58,6 +62,55 @@ __device__ __forceinline__ void pair_separation(const PairArgs &A, int p, int i,
     if (n != 0) dk = dk - A.boxlen[k] * (double)n;
     d[k] = dk;
   }
+}
+
+// oracle A.5b (sh_oracle.c contact_dissipation), same operations in the same order.  out: [2..4] F on i, [5..7] tau_i,
+// [8..10] tau_j, [11..13] overlap centroid (i's periodic image); d = c_i - c_j (minimum image); lj = c_j - x_j.
+__device__ __forceinline__ void contact_dissipation(const PairArgs &A, int i, int j, int shp_i, int shp_j, const double d[3],
+                                                    const double lj[3], double out[14]) {
+  const double gn = A.pgn[shp_i * SH_MAX_SHAPES + shp_j], gt = A.pgt[shp_i * SH_MAX_SHAPES + shp_j], mu = A.pmu[shp_i * SH_MAX_SHAPES + shp_j];
+  if (!(gn > 0.0 || (gt > 0.0 && mu > 0.0))) return;
+  const int st = A.stride;
+  double *F = out + 2, *ti = out + 5, *tj = out + 8;
+  const double *xc = out + 11;
+  const double fn2 = F[0] * F[0] + F[1] * F[1] + F[2] * F[2];
+  if (!(fn2 > 0.0)) return;
+  const double fn = sqrt(fn2);
+  const double nh[3] = {F[0] / fn, F[1] / fn, F[2] / fn};
+  double xi[3], xj[3], vi[3], vj[3], Li[3], Lj[3], qi[4], qj[4], wi[3], wj[3];
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    xi[r] = A.x[r * st + i];
+    xj[r] = (A.c[r * st + i] - d[r]) - lj[r];
+    vi[r] = A.v[r * st + i]; vj[r] = A.v[r * st + j];
+    Li[r] = A.L[r * st + i]; Lj[r] = A.L[r * st + j];
+  }
+#pragma unroll
+  for (int r = 0; r < 4; r++) { qi[r] = A.q[r * st + i]; qj[r] = A.q[r * st + j]; }
+  omega_from_angmom(qi, Li, A.shapes[shp_i].inertia, wi);
+  omega_from_angmom(qj, Lj, A.shapes[shp_j].inertia, wj);
+  const double ri[3] = {xc[0] - xi[0], xc[1] - xi[1], xc[2] - xi[2]}, rj[3] = {xc[0] - xj[0], xc[1] - xj[1], xc[2] - xj[2]};
+  const double vr[3] = {(vi[0] + (wi[1] * ri[2] - wi[2] * ri[1])) - (vj[0] + (wj[1] * rj[2] - wj[2] * rj[1])),
+                        (vi[1] + (wi[2] * ri[0] - wi[0] * ri[2])) - (vj[1] + (wj[2] * rj[0] - wj[0] * rj[2])),
+                        (vi[2] + (wi[0] * ri[1] - wi[1] * ri[0])) - (vj[2] + (wj[0] * rj[1] - wj[1] * rj[0]))};
+  const double vn = vr[0] * nh[0] + vr[1] * nh[1] + vr[2] * nh[2];
+  double fnt = fn - gn * vn;
+  if (fnt < 0.0) fnt = 0.0;
+  double Fd[3] = {(fnt - fn) * nh[0], (fnt - fn) * nh[1], (fnt - fn) * nh[2]};
+  const double vt[3] = {vr[0] - vn * nh[0], vr[1] - vn * nh[1], vr[2] - vn * nh[2]};
+  const double vt2 = vt[0] * vt[0] + vt[1] * vt[1] + vt[2] * vt[2];
+  if (gt > 0.0 && mu > 0.0 && vt2 > 0.0) {
+    const double vtm = sqrt(vt2);
+    double ft = gt * vtm;
+    const double cap = mu * fnt;
+    if (ft > cap) ft = cap;
+    const double sc = ft / vtm;
+    Fd[0] -= sc * vt[0]; Fd[1] -= sc * vt[1]; Fd[2] -= sc * vt[2];
+  }
+#pragma unroll
+  for (int r = 0; r < 3; r++) F[r] += Fd[r];
+  ti[0] += ri[1] * Fd[2] - ri[2] * Fd[1]; ti[1] += ri[2] * Fd[0] - ri[0] * Fd[2]; ti[2] += ri[0] * Fd[1] - ri[1] * Fd[0];
+  tj[0] -= rj[1] * Fd[2] - rj[2] * Fd[1]; tj[1] -= rj[2] * Fd[0] - rj[0] * Fd[2]; tj[2] -= rj[0] * Fd[1] - rj[1] * Fd[0];
 }
 
 __host__ __device__ inline size_t pair_smem_bytes(int max_terms, int max_nq, int nwarps) {
@@ -274,6 +327,7 @@ __global__ void __launch_bounds__(NT) pair_kernel(PairArgs A) {
           out[8 + r] = -pr * Tj[r];
           out[11 + r] = (A.c[r * st + i] - 0.5 * d[r]) + (Gij[r] + Gji[r]) / V;
         }
+        if (A.dissip) contact_dissipation(A, i, j, shp_i, shp_j, d, lj, out);
       }
 #pragma unroll
       for (int r = 0; r < 14; r++) A.pres[(size_t)r * A.pres_stride + p] = out[r];

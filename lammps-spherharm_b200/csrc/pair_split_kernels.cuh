@@ -920,6 +920,7 @@ __global__ void __launch_bounds__(128, 6) pair_reduce_kernel(PairArgs A, SplitAr
             out[8 + r] = -pr * Tj[r];
             out[11 + r] = (A.c[r * st + i] - 0.5 * d[r]) + (Gs[0][r] + Gs[1][r]) / V;
           }
+          if (A.dissip) contact_dissipation(A, i, j, shp_i, shp_j, d, lj, out);
         }
       }
 #pragma unroll

@@ -340,6 +340,7 @@ __global__ void __launch_bounds__(NW * 32) pair_warp_kernel(PairArgs A, int nsha
           out[8 + r] = -pr * Tj[r];
           out[11 + r] = (A.c[r * st + i] - 0.5 * d[r]) + (Gij[r] + Gji[r]) / V;
         }
+        if (A.dissip) contact_dissipation(A, i, j, shp_i, shp_j, d, lj, out);
       }
       if (lane == 0) {
 #pragma unroll

@@ -56,7 +56,9 @@ struct sh_ctx {
   bool shapes_dirty = true;
   int total_terms = 0;
   std::vector<double> pk, pm;  // SH_MAX_SHAPES^2
-  DevBuf<double> d_pk, d_pm;
+  std::vector<double> pgn, pgt, pmu;   // dissipation: normal / tangential damping, Coulomb coefficient
+  bool dissip = false;
+  DevBuf<double> d_pk, d_pm, d_pgn, d_pgt, d_pmu, stress_part;
   bool coeff_dirty = true;
   WallSet walls{};
   double g[3] = {0, 0, 0}, skin = 0.0, dt = 1e-4, gamma_lin = 0.0, gamma_rot = 0.0;
@@ -225,10 +227,14 @@ int upload_shapes(sh_ctx *h) {
 
 int upload_coeffs(sh_ctx *h) {
   if (!h->coeff_dirty) return 0;
-  try { h->d_pk.ensure(SH_MAX_SHAPES * SH_MAX_SHAPES); h->d_pm.ensure(SH_MAX_SHAPES * SH_MAX_SHAPES); }
+  const size_t nn = SH_MAX_SHAPES * SH_MAX_SHAPES;
+  try { h->d_pk.ensure(nn); h->d_pm.ensure(nn); h->d_pgn.ensure(nn); h->d_pgt.ensure(nn); h->d_pmu.ensure(nn); }
   catch (std::string &e) { return fail(h, e); }
-  CU(cudaMemcpy(h->d_pk.p, h->pk.data(), h->pk.size() * sizeof(double), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(h->d_pm.p, h->pm.data(), h->pm.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_pk.p, h->pk.data(), nn * sizeof(double), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_pm.p, h->pm.data(), nn * sizeof(double), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_pgn.p, h->pgn.data(), nn * sizeof(double), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_pgt.p, h->pgt.data(), nn * sizeof(double), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_pmu.p, h->pmu.data(), nn * sizeof(double), cudaMemcpyHostToDevice));
   h->coeff_dirty = false;
   return 0;
 }
@@ -646,6 +652,8 @@ int compute_forces_device(sh_ctx *h) {
     P.pair_i = h->pair_i.p; P.pair_j = h->pair_j.p; P.pair_eij = h->pair_eij.p; P.pair_eji = h->pair_eji.p; P.pair_img = h->pair_img.p;
     P.npairs = h->npairs; P.slot = h->slot.p; P.slot_stride = h->slot_stride; P.pres = h->pres.p; P.pres_stride = h->pres_stride;
     P.pk = h->d_pk.p; P.pm = h->d_pm.p;
+    P.dissip = h->dissip ? 1 : 0; P.v = h->v.p; P.L = h->L.p; P.q = h->q.p; P.pgn = h->d_pgn.p; P.pgt = h->d_pgt.p; P.pmu = h->d_pmu.p;
+    if (h->dissip && h->nghost > 0 && !h->dd.on) return fail(h, "dissipative contact terms need ghost velocities: use the in-library decomposition (sh_dd_init)");
     for (int d = 0; d < 3; d++) { P.boxlen[d] = h->hi[d] - h->lo[d]; P.periodic[d] = h->periodic[d]; }
     P.work_counter = h->scalars.p + 2; P.counters = h->counters.p;
     int maxT = 1, maxq = 32;
@@ -776,6 +784,7 @@ int sh_create(sh_ctx **out, int device_id) {
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return -6; }
   h->pk.assign(SH_MAX_SHAPES * SH_MAX_SHAPES, 1.0);
   h->pm.assign(SH_MAX_SHAPES * SH_MAX_SHAPES, 1.0);
+  h->pgn.assign(SH_MAX_SHAPES * SH_MAX_SHAPES, 0.0); h->pgt.assign(SH_MAX_SHAPES * SH_MAX_SHAPES, 0.0); h->pmu.assign(SH_MAX_SHAPES * SH_MAX_SHAPES, 0.0);
   try {
     h->scalars.ensure(16); h->bbox.ensure(8); h->counters.ensure(16); h->drift.ensure(4);
   } catch (std::string &) { delete h; return -7; }
@@ -799,7 +808,7 @@ int sh_destroy(sh_ctx *h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   for (auto &d : h->shape_dev) { d.Ap.release(); d.ab.release(); d.node.release(); d.row_x.release(); d.cube.release(); d.pf4.release(); for (auto &w : d.cubew) w.release(); }
-  h->d_shapes.release(); h->d_pk.release(); h->d_pm.release();
+  h->d_shapes.release(); h->d_pk.release(); h->d_pm.release(); h->d_pgn.release(); h->d_pgt.release(); h->d_pmu.release(); h->stress_part.release();
   DevBuf<double> *db[] = {&h->x, &h->v, &h->q, &h->L, &h->f, &h->tq, &h->c, &h->Rs, &h->c0, &h->wallf, &h->ewall, &h->ke, &h->bbox, &h->slot, &h->pres};
   for (auto *b : db) b->release();
   DevBuf<int> *ib[] = {&h->shape, &h->cell_of, &h->cell_count, &h->cell_start, &h->cell_fill, &h->cell_atoms, &h->tile_sum, &h->cnt_full,
@@ -968,6 +977,20 @@ int sh_pair_coeff(sh_ctx *h, int si, int sj, double k, double exponent) {
   if (!(k >= 0) || !(exponent >= 1.0)) return fail(h, "pair_coeff: need k >= 0, exponent >= 1");
   h->pk[si * SH_MAX_SHAPES + sj] = h->pk[sj * SH_MAX_SHAPES + si] = k;
   h->pm[si * SH_MAX_SHAPES + sj] = h->pm[sj * SH_MAX_SHAPES + si] = exponent;
+  h->coeff_dirty = true; h->forces_valid = false;
+  return 0;
+}
+
+int sh_pair_dissipation(sh_ctx *h, int si, int sj, double gamma_n, double gamma_t, double mu) {
+  if (si < 0 || sj < 0 || si >= SH_MAX_SHAPES || sj >= SH_MAX_SHAPES) return fail(h, "pair_dissipation: shape out of range");
+  if (!(gamma_n >= 0) || !(gamma_t >= 0) || !(mu >= 0)) return fail(h, "pair_dissipation: need gamma_n, gamma_t, mu >= 0");
+  h->pgn[si * SH_MAX_SHAPES + sj] = h->pgn[sj * SH_MAX_SHAPES + si] = gamma_n;
+  h->pgt[si * SH_MAX_SHAPES + sj] = h->pgt[sj * SH_MAX_SHAPES + si] = gamma_t;
+  h->pmu[si * SH_MAX_SHAPES + sj] = h->pmu[sj * SH_MAX_SHAPES + si] = mu;
+  h->dissip = false;
+  for (size_t k = 0; k < h->pgn.size(); k++) if (h->pgn[k] > 0 || (h->pgt[k] > 0 && h->pmu[k] > 0)) h->dissip = true;
+  const int gv = h->dissip ? 1 : 0;
+  if (gv != h->dd.ghost_vel) { h->dd.ghost_vel = gv; h->dd.borders_ok = false; h->list_valid = false; }   // ghost records change width
   h->coeff_dirty = true; h->forces_valid = false;
   return 0;
 }
@@ -1417,6 +1440,34 @@ int sh_get_energy(const sh_ctx *hc, double *ke_trans, double *ke_rot, double *e_
   if (ke_trans) *ke_trans = kt;
   if (ke_rot) *ke_rot = kr;
   if (e_contact) *e_contact = ec;
+  return 0;
+}
+
+// pressure-tensor sums of this rank (compute pressure in LAMMPS terms): fixed-order two-level reduction, no FP atomics
+int sh_get_stress(const sh_ctx *hc, double virial[9], double kinetic[9]) {
+  sh_ctx *h = const_cast<sh_ctx *>(hc);
+  CU(cudaSetDevice(h->device));
+  const int n = (int)(h->n - h->nghost), np = h->forces_valid ? h->npairs : 0;
+  const int nb_atoms = std::max(1, cdiv(n, 256)), nb_pairs = std::max(1, cdiv(np, 256));
+  try { h->stress_part.ensure((size_t)9 * (nb_atoms + nb_pairs)); } catch (std::string &e) { return fail(h, e); }
+  double K[9] = {0}, W[9] = {0};
+  if (n > 0) {
+    int rc = prepare(h);
+    if (rc) return rc;
+    stress_kinetic_kernel<<<nb_atoms, 256, 0, h->stream>>>(view(h), h->d_shapes.p, h->stress_part.p);
+    h->kernel_launches++;
+  }
+  if (np > 0) {
+    stress_virial_kernel<<<nb_pairs, 256, 0, h->stream>>>(view_all(h), np, n, h->pair_i.p, h->pair_j.p, h->pair_img.p, h->pres.p, h->pres_stride,
+                                                          h->hi[0] - h->lo[0], h->hi[1] - h->lo[1], h->hi[2] - h->lo[2], h->stress_part.p + (size_t)9 * nb_atoms);
+    h->kernel_launches++;
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  std::vector<double> part((size_t)9 * (nb_atoms + nb_pairs), 0.0);
+  CU(cudaMemcpy(part.data(), h->stress_part.p, part.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  if (n > 0) for (int b = 0; b < nb_atoms; b++) for (int k = 0; k < 9; k++) K[k] += part[(size_t)9 * b + k];
+  if (np > 0) for (int b = 0; b < nb_pairs; b++) for (int k = 0; k < 9; k++) W[k] += part[(size_t)9 * (nb_atoms + b) + k];
+  for (int k = 0; k < 9; k++) { if (virial) virial[k] = W[k]; if (kinetic) kinetic[k] = K[k]; }
   return 0;
 }
 

@@ -144,19 +144,6 @@ __global__ void soa_to_aos_kernel(const double *soa, double *aos, int n, int nco
   for (int d = 0; d < ncomp; d++) aos[(size_t)ncomp * i + d] = soa[(size_t)d * stride + i];
 }
 
-__device__ __forceinline__ void omega_from_angmom(const double q[4], const double L[3], const double I[3],
-                                                  double w[3]) {
-  double R[9];
-  quat_to_mat(q, R);
-  double wb[3];
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-    const double lb = R[k] * L[0] + R[3 + k] * L[1] + R[6 + k] * L[2];
-    wb[k] = (I[k] > 0) ? lb / I[k] : 0.0;
-  }
-#pragma unroll
-  for (int r = 0; r < 3; r++) w[r] = R[3 * r] * wb[0] + R[3 * r + 1] * wb[1] + R[3 * r + 2] * wb[2];
-}
 __device__ __forceinline__ void vecquat(const double w[3], const double q[4], double o[4]) {
   o[0] = -w[0] * q[1] - w[1] * q[2] - w[2] * q[3];
   o[1] = q[0] * w[0] + w[1] * q[3] - w[2] * q[2];
@@ -349,6 +336,60 @@ __global__ void energy_kernel(AtomView A, const DevShape *shapes, double *ke /* 
   double L[3] = {A.L[i], A.L[st + i], A.L[2 * st + i]}, w[3];
   omega_from_angmom(q, L, s.inertia, w);
   ke[A.n + i] = 0.5 * (w[0] * L[0] + w[1] * L[1] + w[2] * L[2]);
+}
+
+// ---- pressure-tensor sums (thermo): per-block partial sums in a fixed order, summed on the host in block order ------
+__device__ __forceinline__ void block_sum9(double v[9], double *out /* 9 per block */) {
+  __shared__ double s_part[8][9];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 9; k++) v[k] = warp_sum(v[k]);
+  if (lane == 0) for (int k = 0; k < 9; k++) s_part[warp][k] = v[k];
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    double t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += s_part[w][threadIdx.x];
+    out[(size_t)9 * blockIdx.x + threadIdx.x] = t;
+  }
+}
+__global__ void stress_kinetic_kernel(AtomView A, const DevShape *shapes, double *part) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (i < A.n) {
+    const int st = A.stride;
+    const double m = shapes[A.shape[i]].mass, vv[3] = {A.v[i], A.v[st + i], A.v[2 * st + i]};
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int b = 0; b < 3; b++) v[3 * a + b] = m * vv[a] * vv[b];
+  }
+  block_sum9(v, part);
+}
+// virial[3a+b] = sum_pairs (x_i - x_j)_a F_b (minimum-image centre-of-mass separation, F = force on i); a pair with a
+// ghost counts half (oracle: orc_get_stress)
+__global__ void stress_virial_kernel(AtomView A, int npairs, int nown, const int *pair_i, const int *pair_j, const int *pair_img,
+                                     const double *pres, int pres_stride, double L0, double L1, double L2, double *part) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (p < npairs) {
+    const int i = pair_i[p], j = pair_j[p], st = A.stride, img = pair_img[p];
+    const double Lb[3] = {L0, L1, L2};
+    const double w = j >= nown ? 0.5 : 1.0;
+    double dx[3], F[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      double d = A.c[a * st + i] - A.c[a * st + j];
+      const int n = ((img >> (2 * a)) & 3) - 1;
+      if (n != 0) d = d - Lb[a] * (double)n;
+      dx[a] = d - (A.c[a * st + i] - A.x[a * st + i]) + (A.c[a * st + j] - A.x[a * st + j]);
+      F[a] = pres[(size_t)(2 + a) * pres_stride + p];
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int b = 0; b < 3; b++) v[3 * a + b] = w * dx[a] * F[b];
+  }
+  block_sum9(v, part);
 }
 
 // ---- K0: FP64 FMA-pipe peak -----------------------------------------------------------------------

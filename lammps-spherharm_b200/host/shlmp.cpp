@@ -9,7 +9,7 @@
 // atom_style spherharm <lmax> <n_theta> <n_phi> <shapefile>... ; boundary ; region <id> block ... ;
 // create_box <ntypes> <region> ; create_atoms <type> single x y z ; read_data <file> ; mass/density via
 // `set type <t> density <rho>` ; set atom <id> quat a b c theta | quat/random <seed> ; velocity all set
-// vx vy vz ; velocity <id> set ... ; pair_style spherharm ; pair_coeff i j k exponent ; fix <id> <grp>
+// vx vy vz ; velocity <id> set ... ; pair_style spherharm ; pair_coeff i j k exponent [gamma_n gamma_t mu] ; fix <id> <grp>
 // nve/sh | wall/spherharm <xplane|yplane|zplane> <pos> <k> <exponent> [hi] | gravity <g> vector x y z |
 // viscous <gamma> ; neighbor <skin> bin ; neigh_modify every N [check yes|no] ; timestep ; thermo N ;
 // dump <id> <grp> custom N <file> ... ; run N ; write_restart <file> ; read_restart <file> ; print "..." ;
@@ -120,7 +120,7 @@ struct Shlmp {
   double lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
   int periodic[3] = {1, 1, 1};
   std::map<std::string, std::vector<double>> regions;
-  struct Coeff { int i, j; double k, e; };
+  struct Coeff { int i, j; double k, e, gn, gt, mu; };
   std::vector<Coeff> coeffs;
   struct Wall { double p[3], n[3], k, e; };
   std::vector<Wall> walls;
@@ -181,7 +181,7 @@ struct Shlmp {
       avec.tag.resize(n); avec.type.assign(n, 1); avec.x.resize(3 * n); avec.v.resize(3 * n); avec.quat.resize(4 * n); avec.angmom.resize(3 * n);
       for (int64_t i = 0; i < n; i++) avec.tag[i] = i + 1;
     }
-    for (auto &c : coeffs) ck(sh_pair_coeff(h, c.i - 1, c.j - 1, c.k, c.e));
+    for (auto &c : coeffs) { ck(sh_pair_coeff(h, c.i - 1, c.j - 1, c.k, c.e)); if (c.gn > 0 || c.gt > 0) ck(sh_pair_dissipation(h, c.i - 1, c.j - 1, c.gn, c.gt, c.mu)); }
     for (auto &w : walls) ck(sh_add_wall(h, w.p, w.n, w.k, w.e));
     ck(sh_set_gravity(h, g));
     ck(sh_set_damping(h, gamma, gamma));
@@ -370,7 +370,10 @@ void execute(Shlmp &S, const std::vector<std::string> &t) {
     const int nt = (int)S.avec.shape_files.size();
     auto range = [&](const std::string &s, int &a, int &b) { if (s == "*") { a = 1; b = nt; } else { a = b = std::stoi(s); } if (a < 1 || b > nt) error_all(FLERR, "Incorrect args for pair coefficients"); };
     int i0, i1, j0, j1; range(t[1], i0, i1); range(t[2], j0, j1);
-    for (int i = i0; i <= i1; i++) for (int j = std::max(i, j0); j <= j1; j++) S.coeffs.push_back({i, j, std::stod(t[3]), std::stod(t[4])});
+    double gn = 0, gt = 0, mu = 0;   // optional: pair_coeff i j k exponent gamma_n gamma_t mu (dissipative contact terms)
+    if (t.size() >= 8) { gn = std::stod(t[5]); gt = std::stod(t[6]); mu = std::stod(t[7]); if (gn < 0 || gt < 0 || mu < 0) error_all(FLERR, "Incorrect args for pair coefficients"); }
+    else if (t.size() != 5) error_all(FLERR, "Incorrect args for pair coefficients");
+    for (int i = i0; i <= i1; i++) for (int j = std::max(i, j0); j <= j1; j++) S.coeffs.push_back({i, j, std::stod(t[3]), std::stod(t[4]), gn, gt, mu});
     return;
   }
   if (c == "fix") {

@@ -227,6 +227,12 @@ def apply(sim, cfg):
         for j in ids:
             if j >= i:
                 sim.pair_coeff(i, j, k, e)
+    if cfg.get("dissipation"):
+        gn, gt, mu = cfg["dissipation"]
+        for i in ids:
+            for j in ids:
+                if j >= i:
+                    sim.pair_dissipation(i, j, gn, gt, mu)
     for (pt, nrm, kw, ew) in cfg["walls"]:
         sim.add_wall(pt, nrm, kw, ew)
     sim.set_gravity(cfg["gravity"])

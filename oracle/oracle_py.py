@@ -120,6 +120,14 @@ class Oracle:
     def set_damping(self, gamma_lin, gamma_rot):
         self._ck(self.L.orc_set_damping(self.h, C.c_double(gamma_lin), C.c_double(gamma_rot)))
 
+    def pair_dissipation(self, si, sj, gamma_n, gamma_t, mu):
+        self._ck(self.L.orc_pair_dissipation(self.h, int(si), int(sj), C.c_double(gamma_n), C.c_double(gamma_t), C.c_double(mu)))
+
+    def get_stress(self):
+        w, k = np.zeros(9), np.zeros(9)
+        self._ck(self.L.orc_get_stress(self.h, _p(w), _p(k)))
+        return dict(virial=w.reshape(3, 3), kinetic=k.reshape(3, 3))
+
     def set_shear(self, rate):
         self._ck(self.L.orc_set_shear(self.h, C.c_double(rate)))
 

@@ -48,6 +48,7 @@ struct orc_ctx {
   int n_theta, n_phi;
   int nshape; shape_t shp[MAX_SHAPES];
   double pk[MAX_SHAPES][MAX_SHAPES], pm[MAX_SHAPES][MAX_SHAPES];
+  double gn[MAX_SHAPES][MAX_SHAPES], gt[MAX_SHAPES][MAX_SHAPES], mu[MAX_SHAPES][MAX_SHAPES];   /* dissipation (A.5b) */
   int nwall; wall_t wall[MAX_WALLS];
   double g[3], skin, dt, gamma_lin, gamma_rot; int nthreads;
   int64_t n; int64_t *tag; int *shape;
@@ -66,7 +67,7 @@ orc_ctx *orc_create(void) {
   orc_ctx *c = (orc_ctx *)calloc(1, sizeof *c);
   for (int k = 0; k < 3; k++) { c->lo[k] = -1e30; c->hi[k] = 1e30; }
   c->n_theta = 32; c->n_phi = 64; c->skin = 0.0; c->dt = 1e-4;
-  for (int i = 0; i < MAX_SHAPES; i++) for (int j = 0; j < MAX_SHAPES; j++) { c->pk[i][j] = 1.0; c->pm[i][j] = 1.0; }
+  for (int i = 0; i < MAX_SHAPES; i++) for (int j = 0; j < MAX_SHAPES; j++) { c->pk[i][j] = 1.0; c->pm[i][j] = 1.0; c->gn[i][j] = c->gt[i][j] = c->mu[i][j] = 0.0; }
   c->nthreads = 1;
   return c;
 }
@@ -384,6 +385,12 @@ int orc_pair_coeff(orc_ctx *c, int si, int sj, double k, double m) {
   if (!(k >= 0) || !(m >= 1.0)) return fail(c, "pair_coeff: need k >= 0, exponent >= 1");
   c->pk[si][sj] = c->pk[sj][si] = k; c->pm[si][sj] = c->pm[sj][si] = m; c->forces_valid = 0; return 0;
 }
+int orc_pair_dissipation(orc_ctx *c, int si, int sj, double gamma_n, double gamma_t, double mu) {
+  if (si < 0 || sj < 0 || si >= MAX_SHAPES || sj >= MAX_SHAPES) return fail(c, "pair_dissipation: shape out of range");
+  if (gamma_n < 0 || gamma_t < 0 || mu < 0) return fail(c, "pair_dissipation: negative coefficient");
+  c->gn[si][sj] = c->gn[sj][si] = gamma_n; c->gt[si][sj] = c->gt[sj][si] = gamma_t; c->mu[si][sj] = c->mu[sj][si] = mu;
+  c->forces_valid = 0; return 0;
+}
 int orc_add_wall(orc_ctx *c, const double point[3], const double normal[3], double k, double m) {
   if (c->nwall >= MAX_WALLS) return fail(c, "too many walls");
   double nn = sqrt(normal[0] * normal[0] + normal[1] * normal[1] + normal[2] * normal[2]);
@@ -583,6 +590,47 @@ static double contact_pressure(double k, double m, double V, double *E) {
   return m * k * pw;
 }
 
+static void omega_from_L(const double q[4], const double L[3], const double I[3], double w[3]);
+
+/* A.5b  Dissipative part of the contact law (builder's choice; the reference's is unknown: PARITY UNPINNED).
+ * History-free viscous normal damping + regularised Coulomb friction, applied at the overlap centroid x_c:
+ *   n = F_el / |F_el|  (direction of the elastic force on i),  r_i = x_c - x_i, r_j = x_c - x_j,
+ *   v_rel = (v_i + w_i x r_i) - (v_j + w_j x r_j),  vn = v_rel . n,
+ *   normal magnitude  fnt = max(0, |F_el| - gamma_n vn)   (never attractive),
+ *   tangential        F_t = -min(gamma_t |v_t|, mu fnt) v_t / |v_t|,  v_t = v_rel - vn n,
+ *   F_i = fnt n + F_t = -F_j;  torques  tau_i += r_i x (F_i - F_el),  tau_j -= r_j x (F_i - F_el).
+ * Velocities and angular momenta are the arrays as they stand when the forces are computed (half-step values inside
+ * the velocity-Verlet step).  xj = centre of mass of j in i's periodic image. */
+static void contact_dissipation(double gn, double gt, double mu, const double xi[3], const double xj[3], const double xc[3],
+                                const double vi[3], const double vj[3], const double wi[3], const double wj[3],
+                                double F[3], double ti[3], double tj[3]) {
+  const double fn2 = F[0] * F[0] + F[1] * F[1] + F[2] * F[2];
+  if (!(fn2 > 0.0)) return;
+  const double fn = sqrt(fn2);
+  const double nh[3] = {F[0] / fn, F[1] / fn, F[2] / fn};
+  const double ri[3] = {xc[0] - xi[0], xc[1] - xi[1], xc[2] - xi[2]}, rj[3] = {xc[0] - xj[0], xc[1] - xj[1], xc[2] - xj[2]};
+  const double vr[3] = {(vi[0] + (wi[1] * ri[2] - wi[2] * ri[1])) - (vj[0] + (wj[1] * rj[2] - wj[2] * rj[1])),
+                        (vi[1] + (wi[2] * ri[0] - wi[0] * ri[2])) - (vj[1] + (wj[2] * rj[0] - wj[0] * rj[2])),
+                        (vi[2] + (wi[0] * ri[1] - wi[1] * ri[0])) - (vj[2] + (wj[0] * rj[1] - wj[1] * rj[0]))};
+  const double vn = vr[0] * nh[0] + vr[1] * nh[1] + vr[2] * nh[2];
+  double fnt = fn - gn * vn;
+  if (fnt < 0.0) fnt = 0.0;
+  double Fd[3] = {(fnt - fn) * nh[0], (fnt - fn) * nh[1], (fnt - fn) * nh[2]};
+  const double vt[3] = {vr[0] - vn * nh[0], vr[1] - vn * nh[1], vr[2] - vn * nh[2]};
+  const double vt2 = vt[0] * vt[0] + vt[1] * vt[1] + vt[2] * vt[2];
+  if (gt > 0.0 && mu > 0.0 && vt2 > 0.0) {
+    const double vtm = sqrt(vt2);
+    double ft = gt * vtm;
+    const double cap = mu * fnt;
+    if (ft > cap) ft = cap;
+    const double sc = ft / vtm;
+    Fd[0] -= sc * vt[0]; Fd[1] -= sc * vt[1]; Fd[2] -= sc * vt[2];
+  }
+  for (int r = 0; r < 3; r++) F[r] += Fd[r];
+  ti[0] += ri[1] * Fd[2] - ri[2] * Fd[1]; ti[1] += ri[2] * Fd[0] - ri[0] * Fd[2]; ti[2] += ri[0] * Fd[1] - ri[1] * Fd[0];
+  tj[0] -= rj[1] * Fd[2] - rj[2] * Fd[1]; tj[1] -= rj[2] * Fd[0] - rj[0] * Fd[2]; tj[2] -= rj[0] * Fd[1] - rj[1] * Fd[0];
+}
+
 /* ---------------- forces: pairs (A.4, A.5), walls (A.6), gather ---------------- */
 int orc_compute_forces(orc_ctx *c) {
   if (c->n > 0 && c->nshape == 0) return fail(c, "no shapes");
@@ -619,6 +667,20 @@ int orc_compute_forces(orc_ctx *c) {
     for (int r = 0; r < 3; r++) {
       pr->ti[r] = -p * Ti[r]; pr->tj[r] = -p * Tj[r];
       pr->xc[r] = (c->c[3 * i + r] - 0.5 * d[r]) + (ij.G[r] + ji.G[r]) / V;
+    }
+    const double gn = c->gn[c->shape[i]][c->shape[j]], gt = c->gt[c->shape[i]][c->shape[j]], mu = c->mu[c->shape[i]][c->shape[j]];
+    if (gn > 0.0 || (gt > 0.0 && mu > 0.0)) {
+      double xj[3], wi[3], wj[3];
+      for (int r = 0; r < 3; r++) xj[r] = (c->c[3 * i + r] - d[r]) - lj[r];       /* j's centre of mass in i's image */
+      omega_from_L(&c->q[4 * i], &c->L[3 * i], si->inertia, wi);
+      omega_from_L(&c->q[4 * j], &c->L[3 * j], sj->inertia, wj);
+      double vj[3] = {c->v[3 * j], c->v[3 * j + 1], c->v[3 * j + 2]};
+      if (c->shear_rate != 0.0) {   /* the image of j that i touches moves with the sheared cell it sits in */
+        const double Ly = c->hi[1] - c->lo[1];
+        const double ny = rint((c->c[3 * i + 1] - c->c[3 * j + 1]) / Ly);
+        vj[0] += ny * c->shear_rate * Ly;
+      }
+      contact_dissipation(gn, gt, mu, &c->x[3 * i], xj, pr->xc, &c->v[3 * i], vj, wi, wj, pr->F, pr->ti, pr->tj);
     }
   }
   c->cnt_pairs += c->npair; c->cnt_trans += ctr; c->cnt_eval += cev; c->cnt_inside += cin;
@@ -841,6 +903,33 @@ int orc_get_energy(const orc_ctx *c, double *ke_trans, double *ke_rot, double *e
     kr += 0.5 * (w[0] * c->L[3 * i] + w[1] * c->L[3 * i + 1] + w[2] * c->L[3 * i + 2]);
   }
   if (ke_trans) *ke_trans = kt; if (ke_rot) *ke_rot = kr; if (e_contact) *e_contact = c->e_contact;
+  return 0;
+}
+
+/* Pressure-tensor sums (compute pressure / stress/atom in LAMMPS terms): kinetic[3a+b] = sum_i m v_a v_b over owned
+ * atoms, virial[3a+b] = sum_pairs (x_i - x_j)_a F_b with the minimum-image centre-of-mass separation and F = force on i;
+ * a pair with a ghost counts half (the owner rank of the ghost adds the other half).  Walls are not included.
+ * pressure tensor = (kinetic + virial) / volume. */
+int orc_get_stress(const orc_ctx *c, double virial[9], double kinetic[9]) {
+  double W[9] = {0}, K[9] = {0};
+  const int64_t nown = c->n - c->nghost;
+  for (int64_t i = 0; i < nown; i++) {
+    const double m = c->shp[c->shape[i]].mass, *v = &c->v[3 * i];
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) K[3 * a + b] += m * v[a] * v[b];
+  }
+  if (c->forces_valid)
+    for (int64_t p = 0; p < c->npair; p++) {
+      const pairres_t *pr = &c->pr[p];
+      const int i = pr->i, j = pr->j;
+      double d[3] = {c->c[3 * i] - c->c[3 * j], c->c[3 * i + 1] - c->c[3 * j + 1], c->c[3 * i + 2] - c->c[3 * j + 2]};
+      min_image(c, d);
+      const double w = j >= nown ? 0.5 : 1.0;
+      for (int a = 0; a < 3; a++) {
+        const double dx = d[a] - (c->c[3 * i + a] - c->x[3 * i + a]) + (c->c[3 * j + a] - c->x[3 * j + a]);   /* x_i - x_j */
+        for (int b = 0; b < 3; b++) W[3 * a + b] += w * dx * pr->F[b];
+      }
+    }
+  for (int k = 0; k < 9; k++) { if (virial) virial[k] = W[k]; if (kinetic) kinetic[k] = K[k]; }
   return 0;
 }
 

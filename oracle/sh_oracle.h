@@ -42,6 +42,10 @@ int orc_set_gravity(orc_ctx *c, const double g[3]);
 int orc_set_neighbor(orc_ctx *c, double skin, int every, int check);
 int orc_set_timestep(orc_ctx *c, double dt);
 int orc_set_damping(orc_ctx *c, double gamma_lin, double gamma_rot);
+/* dissipative contact terms (A.5b): viscous normal damping gamma_n, tangential gamma_t capped by Coulomb mu */
+int orc_pair_dissipation(orc_ctx *c, int shape_i, int shape_j, double gamma_n, double gamma_t, double mu);
+/* pressure-tensor sums: kinetic = sum m v v (owned atoms), virial = sum_pairs (x_i - x_j) F_i (row-major 3x3) */
+int orc_get_stress(const orc_ctx *c, double virial[9], double kinetic[9]);
 /* Lees-Edwards shear: flow along x, gradient along y, rate = dvx/dy; after orc_set_box */
 int orc_set_shear(orc_ctx *c, double rate);
 int orc_set_threads(orc_ctx *c, int nthreads);

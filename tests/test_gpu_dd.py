@@ -171,3 +171,25 @@ def test_lees_edwards_shear_box_vs_oracle(variant):
     assert info["nghost"] > 0 and info["border_builds"] >= 3
     assert np.abs(ny).max() >= 1            # some atoms did cross the sheared boundary
     g.close(); o.close()
+
+
+def test_self_ghost_decomposition_with_dissipation():
+    """Ghosts carry v and angmom when the contact law depends on velocities (13 doubles per ghost instead of 7)."""
+    cfg = _cfg()
+    rng = np.random.default_rng(3)
+    cfg["angmom"] = rng.normal(0, 0.5, size=cfg["angmom"].shape)
+    cfg["dissipation"] = (3.0, 2.0, 0.4)
+    ref = pkg.ShGpu(); W.apply(ref, cfg)
+    dd = pkg.ShGpu(); dd.set_tuning("dd_self_ghosts", 1); dd.dd_init(0, 1); W.apply(dd, cfg)
+    ref.compute_forces(); dd.compute_forces()
+    r0 = ref.get_atoms(); d0, info = _sorted_owned(dd)
+    fs = np.abs(r0["f"]).max()
+    assert np.abs(d0["f"] - r0["f"]).max() <= 1e-11 * fs and np.abs(d0["torque"] - r0["torque"]).max() <= 1e-11 * fs
+    ref.run(200); dd.run(200)
+    r1 = ref.get_atoms(); d1, info = _sorted_owned(dd)
+    L = np.asarray(cfg["box"][1]) - np.asarray(cfg["box"][0])
+    dx = d1["x"] - r1["x"]; dx -= L * np.rint(dx / L)
+    assert np.abs(dx).max() <= 1e-9 and np.abs(d1["angmom"] - r1["angmom"]).max() <= 1e-8
+    sr, sd = ref.get_stress(), dd.get_stress()
+    assert np.abs(sr["virial"] - sd["virial"]).max() <= 1e-8 * np.abs(sr["virial"]).max()
+    ref.close(); dd.close()

@@ -206,3 +206,57 @@ def test_lees_edwards_image_equals_explicit_placement():
     assert np.abs(f1 - f2).max() <= 1e-10 * np.abs(f2).max()
     t1, t2 = o1.get_atoms()["torque"], o2.get_atoms()["torque"]
     assert np.abs(t1 - t2).max() <= 1e-10 * np.abs(f2).max()
+
+
+def test_dissipative_contact_two_spheres():
+    """A.5b on two spheres: the normal damping adds gamma_n * approach speed along the line of centres, the friction is
+    min(gamma_t |v_t|, mu F_n) against the tangential relative velocity, and its torque is r x F_t on both particles."""
+    a, b = W.sphere_shape(4, 1.0)
+    def run(gn, gt, mu, vi, Li=(0, 0, 0)):
+        o = O.Oracle()
+        o.set_quadrature(48, 96)
+        sid = o.add_shape(4, a, b, 1.0)
+        x = np.array([[-0.95, 0, 0], [0.95, 0, 0.0]])
+        o.set_atoms(np.zeros(2, np.int32), x, np.array([vi, [0, 0, 0]], float), None, np.array([Li, [0, 0, 0]], float))
+        o.pair_coeff(sid, sid, 1e3, 1.0)
+        o.pair_dissipation(sid, sid, gn, gt, mu)
+        o.set_neighbor(0.1)
+        o.compute_forces()
+        return o.get_atoms()
+    el = run(0, 0, 0, (0.3, 0.2, 0))
+    fn = -el["f"][0, 0]
+    assert fn > 1.0 and abs(el["f"][0, 1]) < 1e-9 * fn
+    # normal damping only: approaching at 0.3 along x
+    nd = run(5.0, 0, 0, (0.3, 0.2, 0))
+    assert abs(-nd["f"][0, 0] - (fn + 5.0 * 0.3)) < 1e-9 * fn
+    assert np.abs(nd["f"][0] + nd["f"][1]).max() < 1e-12 * fn
+    # separating fast: the normal force is clamped at zero, never attractive
+    sep = run(1e6, 0, 0, (-0.3, 0, 0))
+    assert np.abs(sep["f"]).max() < 1e-9 * fn
+    # viscous branch of the friction: gamma_t |v_t| < mu F_n
+    ft = run(0, 2.0, 0.5, (0.0, 0.2, 0))
+    assert abs(ft["f"][0, 1] + 2.0 * 0.2) < 1e-9 and abs(ft["f"][1, 1] - 2.0 * 0.2) < 1e-9
+    # torque = r x F_t with r = (+-0.95, 0, 0) from each centre to the centroid at the origin
+    assert abs(ft["torque"][0, 2] - 0.95 * ft["f"][0, 1]) < 1e-6 and abs(ft["torque"][1, 2] - 0.95 * ft["f"][0, 1]) < 1e-6
+    # Coulomb branch: gamma_t |v_t| > mu F_n
+    fc = run(0, 1e6, 0.3, (0.0, 0.2, 0))
+    assert abs(fc["f"][0, 1] + 0.3 * fn) < 1e-9 * fn
+    # rolling contact: the surface velocity of a spinning sphere enters v_rel (w x r)
+    I = 0.4 * (4.0 / 3.0 * np.pi) * 1.0     # 2/5 m R^2, unit density and radius
+    sp = run(0, 2.0, 10.0, (0, 0, 0), Li=(0, 0, I * 0.7))           # w_z = 0.7 -> v at the contact = w x r = (0, 0.7 * 0.95, 0)
+    assert abs(sp["f"][0, 1] + 2.0 * 0.7 * 0.95) < 2e-3
+
+
+def test_stress_sums_two_particles():
+    a, b = W.sphere_shape(4, 1.0)
+    o = O.Oracle(); o.set_quadrature(32, 64)
+    sid = o.add_shape(4, a, b, 2.0)
+    x = np.array([[-0.9, 0.1, 0], [0.9, 0, 0.0]]); v = np.array([[0.5, 0, 0.2], [0, -0.3, 0]])
+    o.set_atoms(np.zeros(2, np.int32), x, v, None, None)
+    o.pair_coeff(sid, sid, 1e3, 1.0); o.set_neighbor(0.1); o.compute_forces()
+    st, at = o.get_stress(), o.get_atoms()
+    m = 2.0 * 4.0 / 3.0 * np.pi
+    K = sum(m * np.outer(v[i], v[i]) for i in range(2))
+    assert np.abs(st["kinetic"] - K).max() < 1e-6 * np.abs(K).max()
+    Wv = np.outer(x[0] - x[1], at["f"][0])
+    assert np.abs(st["virial"] - Wv).max() < 1e-12 * np.abs(Wv).max()
