@@ -1115,9 +1115,10 @@ int step_once(sh_ctx *h) {
   bool decided = false;
   if (!due) decided = true;
   else if (!h->neigh_check) { rebuild = 1; decided = true; }
-  if (lag) {
-    int pred = 0;
-    if (h->lag_pending) { CU(cudaEventSynchronize(h->ev_lag[h->lag_slot])); pred = h->h_lagflag[h->lag_slot]; h->lag_pending = false; }
+  if (lag && h->lag_pending) {   // no prediction in flight (first step, or the step after a rebuild): classic decision below
+    CU(cudaEventSynchronize(h->ev_lag[h->lag_slot]));
+    const int pred = h->h_lagflag[h->lag_slot];
+    h->lag_pending = false;
     if (!decided) { rebuild = pred; decided = true; }
   }
   if ((rc = launch_integrate_initial(h, decided && !rebuild))) return rc;

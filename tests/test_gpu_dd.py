@@ -144,6 +144,7 @@ def test_lees_edwards_shear_box_vs_oracle(variant):
     import oracle_py as O
     rate = 0.6
     cfg = W.shear_box(W.packing((5, 4, 4), 20, (32, 64), nshapes=4, seed=33, periodic=True, name="le", skin=0.04, vel_sigma=0.3, dt=4e-4), rate)
+    cfg["v"] = cfg["v"] + np.array([0.0, 8.0, 0.0])      # a drift along the gradient direction: atoms cross the sheared boundary
     lo, hi, _ = cfg["box"]
     L = np.asarray(hi) - np.asarray(lo)
     g = pkg.ShGpu(); W.apply(g, cfg); g.set_pair_tuning(0, 0, variant)
