@@ -165,6 +165,9 @@ int sh_set_pair_tuning(sh_ctx *h, int threads_per_cta, int ctas_per_sm, int vari
  * "cube_n" direction cells per cube-face edge of the per-shape bound tables (8..144, default 144; before sh_add_shape);
  * "sync_rebuild" 1 = sh_run decides neighbor rebuilds from the current step's displacement flag (one host round trip per
  * step) instead of the one-step-ahead prediction (default 0: the host never waits for the device inside sh_run);
+ * "newton" (in-library decomposition; default 1) 1 = a pair that straddles a rank boundary is evaluated by one rank (chosen
+ * from the two tags) and the force / torque on the ghost is returned to its owner every step (reverse communication, 48 B
+ * per ghost); 0 = both ranks evaluate it and keep their own half (no return trip);
  * "step_trace" 1 = record a CUDA event per step in sh_run (sh_get_step_trace);
  * "dd_self_ghosts" 1 = (testing) with the decomposition on, periodic dimensions are served by ghost images even when they
  * are not divided, so that one GPU exercises migration, border lists and the ghost exchange against itself */

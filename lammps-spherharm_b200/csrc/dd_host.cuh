@@ -332,6 +332,16 @@ int dd_borders(sh_ctx *h) {
     h->kernel_launches += 2;
   }
   if ((rc2 = dd_sendrecv(h, D.nbr_rank, D.sendbuf.p, D.send_cnt, D.recvbuf.p, D.recv_cnt, wf))) return rc2;
+  // reverse communication: where in the send list every owned atom appears
+  try { D.rev_cnt.ensure((size_t)nown + 2); D.rev_off.ensure((size_t)nown + 2); D.rev_k.ensure((size_t)std::max(nsend, 1)); }
+  catch (std::string &e) { return fail(h, e); }
+  if (nown > 0) {
+    if (nslot > 0) dd_rev_count_kernel<<<cdiv(nown, 256), 256, 0, h->stream>>>(nown, nslot, D.flag.p, D.rev_cnt.p);
+    else CU(cudaMemsetAsync(D.rev_cnt.p, 0, (size_t)nown * sizeof(int), h->stream));
+    if (exclusive_scan(h, D.rev_cnt.p, D.rev_off.p, nown, h->scalars.p)) return -1;
+    if (nslot > 0 && nsend > 0) dd_rev_fill_kernel<<<cdiv(nown, 256), 256, 0, h->stream>>>(nown, nslot, D.flag.p, D.pos.p, D.rev_off.p, D.rev_k.p);
+    h->kernel_launches += 2;
+  }
   h->n = nown + nghost; h->nghost = nghost;
   if (nghost > 0) {
     AtomView All = view_all(h);
@@ -361,6 +371,28 @@ int dd_forward(sh_ctx *h) {
   if ((rc2 = dd_sendrecv(h, D.nbr_rank, D.sendbuf.p, D.send_cnt, D.recvbuf.p, D.recv_cnt, w))) return rc2;
   if (h->nghost > 0) {
     dd_unpack_kernel<<<cdiv(h->nghost, 256), 256, 0, h->stream>>>(view_all(h), h->d_tag.p, nown, (int)h->nghost, 0, D.ghost_vel, D.recvbuf.p);
+    h->kernel_launches++;
+  }
+  ev_tock(h);
+  return 0;
+}
+
+// reverse_comm (newton on): f / torque gathered on the ghosts return to their owners and are added in a fixed order
+int dd_reverse(sh_ctx *h) {
+  DdCtx &D = h->dd;
+  if (D.nsend == 0 && h->nghost == 0) return 0;
+  const int nown = (int)(h->n - h->nghost), ng = (int)h->nghost;
+  if (ev_tick(h, 6)) return -2;
+  try { D.sendbuf.ensure((size_t)6 * std::max(ng, 1)); D.recvbuf.ensure((size_t)6 * std::max(D.nsend, 1)); }
+  catch (std::string &e) { return fail(h, e); }
+  if (ng > 0) {
+    dd_pack_ghost_forces_kernel<<<cdiv(ng, 256), 256, 0, h->stream>>>(view_all(h), nown, ng, D.sendbuf.p);
+    h->kernel_launches++;
+  }
+  int rc2;
+  if ((rc2 = dd_sendrecv(h, D.nbr_rank, D.sendbuf.p, D.recv_cnt, D.recvbuf.p, D.send_cnt, 6))) return rc2;
+  if (D.nsend > 0 && nown > 0) {
+    dd_add_returned_forces_kernel<<<cdiv(nown, 256), 256, 0, h->stream>>>(view(h), D.rev_off.p, D.rev_k.p, D.recvbuf.p);
     h->kernel_launches++;
   }
   ev_tock(h);

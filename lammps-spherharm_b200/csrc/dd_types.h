@@ -38,6 +38,8 @@ struct DdCtx {
   std::vector<int> send_cnt, recv_cnt;           // ghosts per neighbour rank of the forward exchange
   std::vector<double> base_shift;                // periodic shift per slot (without the Lees-Edwards offset)
   int nsend = 0, ghost_vel = 0;
+  bool newton = true;                            // cross-rank pairs evaluated once, reactions returned (reverse comm)
+  DevBuf<int> rev_cnt, rev_off, rev_k;           // per owned atom: its positions in the send list (ascending slot order)
   bool self_ghosts = false;                      // test knob: periodic dims get ghost images even when undivided
   double le_rate = 0, le_off_build = 0, le_time_build = 0;   // Lees-Edwards: shear rate, image offset at the last rebuild
   DevBuf<int> flag, pos, order, d_int, send_idx, send_slot, shape2;

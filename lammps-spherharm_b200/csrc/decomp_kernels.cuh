@@ -189,6 +189,47 @@ __global__ void dd_unpack_kernel(AtomView A, long long *tag, int first, int m, i
   }
 }
 
+// ---- reverse communication (newton on): force / torque collected on ghosts go back to the owners ------------------
+// per owned atom: in how many slots it is sent, and (after the scan) its positions in the send list in slot order
+__global__ void dd_rev_count_kernel(int nown, int nslot, const int *flag, int *cnt) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nown) return;
+  int c = 0;
+  for (int s = 0; s < nslot; s++) c += flag[(size_t)s * nown + a];
+  cnt[a] = c;
+}
+__global__ void dd_rev_fill_kernel(int nown, int nslot, const int *flag, const int *pos, const int *rev_off, int *rev_k) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nown) return;
+  int e = rev_off[a];
+  for (int s = 0; s < nslot; s++) if (flag[(size_t)s * nown + a]) rev_k[e++] = pos[(size_t)s * nown + a];
+}
+__global__ void dd_pack_ghost_forces_kernel(AtomView A, int first, int m, double *out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m) return;
+  const int i = first + k, st = A.stride;
+#pragma unroll
+  for (int d = 0; d < 3; d++) { out[6 * (size_t)k + d] = A.f[d * st + i]; out[6 * (size_t)k + 3 + d] = A.tq[d * st + i]; }
+}
+// fixed order per atom (ascending slot): bitwise reproducible
+__global__ void dd_add_returned_forces_kernel(AtomView A, const int *rev_off, const int *rev_k, const double *in) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= A.n) return;
+  const int e0 = rev_off[a], e1 = rev_off[a + 1];
+  if (e0 == e1) return;
+  const int st = A.stride;
+  double acc[6];
+#pragma unroll
+  for (int d = 0; d < 3; d++) { acc[d] = A.f[d * st + a]; acc[3 + d] = A.tq[d * st + a]; }
+  for (int e = e0; e < e1; e++) {
+    const double *r = in + 6 * (size_t)rev_k[e];
+#pragma unroll
+    for (int d = 0; d < 6; d++) acc[d] += r[d];
+  }
+#pragma unroll
+  for (int d = 0; d < 3; d++) { A.f[d * st + a] = acc[d]; A.tq[d * st + a] = acc[3 + d]; }
+}
+
 // ---- candidate-cache carry-over across a decomposed rebuild ---------------------------------------------------------
 __device__ __forceinline__ unsigned dd_hash_tag(long long t) {
   unsigned long long z = (unsigned long long)t * 0x9E3779B97F4A7C15ull;

@@ -159,38 +159,57 @@ __device__ __forceinline__ void for_each_neighbor(const double *c, const int *sh
       }
 }
 
-__global__ void nbr_count_kernel(const double *c, const int *shape, const DevShape *shapes, int n, int stride,
-                                 BinGrid G, const int *cell_of, const int *cell_start, const int *cell_atoms,
+// Which atoms are neighbours of row a.  newton off (tags == nullptr): rows exist for owned atoms only and every
+// neighbour counts (a pair that straddles a rank boundary is evaluated by both ranks, each keeps its own half).
+// newton on: a pair with a ghost is evaluated by exactly ONE rank, chosen from the two tags (the owner of the smaller tag
+// when their sum is even, of the larger one when odd: balanced and symmetric); the ghost then needs a row of its own to
+// collect the reaction, which is sent back to its owner (reverse communication).
+__device__ __forceinline__ bool pair_is_mine(long long tag_owned, long long tag_ghost) {
+  const bool owned_is_smaller = tag_owned < tag_ghost;
+  return (((tag_owned + tag_ghost) & 1LL) == 0) == owned_is_smaller;
+}
+__device__ __forceinline__ bool nbr_included(int a, int b, int nown, const long long *tags) {
+  if (!tags) return true;                          // newton off: a is owned
+  const bool ga = a >= nown, gb = b >= nown;
+  if (!ga && !gb) return true;
+  if (ga && gb) return false;
+  return ga ? pair_is_mine(tags[b], tags[a]) : pair_is_mine(tags[a], tags[b]);
+}
+__global__ void nbr_count_kernel(const double *c, const int *shape, const DevShape *shapes, int nrows, int nown, const long long *tags,
+                                 int stride, BinGrid G, const int *cell_of, const int *cell_start, const int *cell_atoms,
                                  int *cnt_full, int *cnt_half) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= nrows) return;
   int nf = 0, nh = 0;
-  for_each_neighbor(c, shape, shapes, stride, G, cell_of, cell_start, cell_atoms, i, [&](int j, int) { nf++; nh += (j > i); });
+  for_each_neighbor(c, shape, shapes, stride, G, cell_of, cell_start, cell_atoms, i, [&](int j, int) {
+    if (nbr_included(i, j, nown, tags)) { nf++; nh += (i < nown && j > i); }
+  });
   cnt_full[i] = nf;
   cnt_half[i] = nh;
 }
-__global__ void nbr_fill_kernel(const double *c, const int *shape, const DevShape *shapes, int n, int stride,
-                                BinGrid G, const int *cell_of, const int *cell_start, const int *cell_atoms,
+__global__ void nbr_fill_kernel(const double *c, const int *shape, const DevShape *shapes, int nrows, int nown, const long long *tags,
+                                int stride, BinGrid G, const int *cell_of, const int *cell_start, const int *cell_atoms,
                                 const int *nbr_off, const int *half_off, int *nbr_j, int *pair_i, int *pair_j,
                                 int *pair_eij, int *pair_img) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= nrows) return;
   int e = nbr_off[i], h = half_off[i];
   for_each_neighbor(c, shape, shapes, stride, G, cell_of, cell_start, cell_atoms, i, [&](int j, int img) {
+    if (!nbr_included(i, j, nown, tags)) return;
     nbr_j[e] = j;
-    if (j > i) { pair_i[h] = i; pair_j[h] = j; pair_eij[h] = e; pair_img[h] = img; h++; }
+    if (i < nown && j > i) { pair_i[h] = i; pair_j[h] = j; pair_eij[h] = e; pair_img[h] = img; h++; }
     e++;
   });
 }
-// reverse CSR entry of every pair.  Only OWNED atoms (index < nown) have CSR rows: for an owned-ghost pair there is no
-// reverse entry (the ghost's force belongs to another rank) and nbr_off[j] must not be read at all.
-__global__ void pair_reverse_kernel(int npairs, int nown, const int *pair_i, const int *pair_j, const int *nbr_off,
+// reverse CSR entry of every pair.  Only atoms with index < nrows have CSR rows (newton off: the owned atoms; for an
+// owned-ghost pair there is then no reverse entry and nbr_off[j] must not be read at all).
+__global__ void pair_reverse_kernel(int npairs, int nrows, const int *pair_i, const int *pair_j, const int *nbr_off,
                                     const int *nbr_j, int *pair_eji) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= npairs) return;
   const int i = pair_i[p], j = pair_j[p];
   int found = -1;
-  if (j < nown)
+  if (j < nrows)
     for (int e = nbr_off[j]; e < nbr_off[j + 1]; e++)
       if (nbr_j[e] == i) { found = e; break; }
   pair_eji[p] = found;

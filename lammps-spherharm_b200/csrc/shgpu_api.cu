@@ -129,7 +129,7 @@ struct sh_ctx {
   DevBuf<double> cc0, cq0, drift;
   bool eval_pending = false;
   DevBuf<unsigned long long> counters;
-  int npairs = 0, nentries = 0;
+  int npairs = 0, nentries = 0, nrows = 0;   // nrows: atoms with CSR rows (owned; owned + ghost with newton on)
   int slot_stride = 0, pres_stride = 0;
   int *h_pinned = nullptr;  // [0] total/flag scratch
   bool forces_valid = false, list_valid = false;
@@ -333,13 +333,18 @@ int build_neighbors(sh_ctx *h) {
   if (exclusive_scan(h, h->cell_count.p, h->cell_start.p, (int)ncell, h->scalars.p)) return -1;
   bin_fill_kernel<<<nb, 256, 0, h->stream>>>(n, h->cell_of.p, h->cell_start.p, h->cell_fill.p, h->cell_atoms.p);
   bin_sort_kernel<<<cdiv(ncell, 256), 256, 0, h->stream>>>((int)ncell, h->cell_start.p, h->cell_atoms.p);
-  const int nbo = std::max(1, cdiv(nown, 256));
-  nbr_count_kernel<<<nbo, 256, 0, h->stream>>>(h->c.p, h->shape.p, h->d_shapes.p, nown, st, G, h->cell_of.p, h->cell_start.p,
+  // newton on (in-library decomposition): ghosts get rows too (they collect the reactions that go back to their owners)
+  const bool newton = h->dd.on && h->dd.newton && h->nghost > 0;
+  const int nrows = newton ? n : nown;
+  const long long *ntags = newton ? h->d_tag.p : nullptr;
+  h->nrows = nrows;
+  const int nbo = std::max(1, cdiv(nrows, 256));
+  nbr_count_kernel<<<nbo, 256, 0, h->stream>>>(h->c.p, h->shape.p, h->d_shapes.p, nrows, nown, ntags, st, G, h->cell_of.p, h->cell_start.p,
                                               h->cell_atoms.p, h->cnt_full.p, h->cnt_half.p);
   h->kernel_launches += 4;
   int nentries = 0, npairs = 0;
-  if (exclusive_scan(h, h->cnt_full.p, h->nbr_off.p, nown, h->scalars.p + 8)) return -1;
-  if (exclusive_scan(h, h->cnt_half.p, h->half_off.p, nown, h->scalars.p + 9)) return -1;
+  if (exclusive_scan(h, h->cnt_full.p, h->nbr_off.p, nrows, h->scalars.p + 8)) return -1;
+  if (exclusive_scan(h, h->cnt_half.p, h->half_off.p, nrows, h->scalars.p + 9)) return -1;
   CU(cudaMemcpyAsync(h->h_pinned, h->scalars.p + 8, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));   // the one host
   CU(cudaStreamSynchronize(h->stream));                                                                     // sync of a rebuild
   nentries = h->h_pinned[0]; npairs = h->h_pinned[1];
@@ -349,10 +354,10 @@ int build_neighbors(sh_ctx *h) {
     if ((size_t)nentries + 1 > (size_t)h->slot_stride) { h->slot_stride = (int)((nentries + 1) * 1.25) + 64; h->slot.release(); h->slot.ensure((size_t)6 * h->slot_stride); }
     if ((size_t)npairs + 1 > (size_t)h->pres_stride) { h->pres_stride = (int)((npairs + 1) * 1.25) + 64; h->pres.release(); h->pres.ensure((size_t)14 * h->pres_stride); }
   } catch (std::string &e) { return fail(h, e); }
-  nbr_fill_kernel<<<nbo, 256, 0, h->stream>>>(h->c.p, h->shape.p, h->d_shapes.p, nown, st, G, h->cell_of.p, h->cell_start.p,
+  nbr_fill_kernel<<<nbo, 256, 0, h->stream>>>(h->c.p, h->shape.p, h->d_shapes.p, nrows, nown, ntags, st, G, h->cell_of.p, h->cell_start.p,
                                              h->cell_atoms.p, h->nbr_off.p, h->half_off.p, h->nbr_j.p, h->pair_i.p,
                                              h->pair_j.p, h->pair_eij.p, h->pair_img.p);
-  pair_reverse_kernel<<<std::max(1, cdiv(npairs, 256)), 256, 0, h->stream>>>(npairs, nown, h->pair_i.p, h->pair_j.p, h->nbr_off.p,
+  pair_reverse_kernel<<<std::max(1, cdiv(npairs, 256)), 256, 0, h->stream>>>(npairs, nrows, h->pair_i.p, h->pair_j.p, h->nbr_off.p,
                                                                              h->nbr_j.p, h->pair_eji.p);
   copy_origin_kernel<<<nb, 256, 0, h->stream>>>(h->c.p, h->c0.p, n, st);
   h->kernel_launches += 3;
@@ -643,9 +648,10 @@ int run_split_pipeline(sh_ctx *h, PairArgs &P) {
 
 int compute_forces_device(sh_ctx *h) {
   const int n = (int)(h->n - h->nghost);   // forces are accumulated on owned atoms only
-  if (n == 0) { h->forces_valid = true; return 0; }
+  const bool newton_dd = h->dd.on && h->dd.newton && h->dd.borders_ok && h->dd.nranks >= 1 && (h->nghost > 0 || h->dd.nsend > 0);
+  if (n == 0 && !newton_dd) { h->forces_valid = true; return 0; }
   AtomView A = view(h);
-  const int nb = cdiv(n, 256);
+  const int nb = std::max(1, cdiv(n, 256));
   if (h->npairs > 0) {
     PairArgs P;
     P.shapes = h->d_shapes.p; P.c = h->c.p; P.Rs = h->Rs.p; P.x = h->x.p; P.shape = h->shape.p; P.stride = h->stride;
@@ -681,12 +687,19 @@ int compute_forces_device(sh_ctx *h) {
     h->ev_used += 2;
     h->pair_launches++; h->kernel_launches++;
   }
-  if (h->walls.n > 0) {
+  if (h->walls.n > 0 && n > 0) {
     wall_kernel<<<cdiv((int64_t)n * 32, 256), 256, 0, h->stream>>>(A, h->d_shapes.p, h->walls, h->ewall.p);
     h->kernel_launches++;
   }
-  gather_kernel<<<nb, 256, 0, h->stream>>>(A, h->nbr_off.p, h->slot.p, h->slot_stride, h->walls.n > 0);
-  h->kernel_launches++;
+  // newton on: the ghosts have rows too, holding the reactions of the cross-rank pairs evaluated here
+  const int nrows = h->list_valid && h->nrows > n ? h->nrows : n;
+  if (nrows > 0) {
+    AtomView G2 = view_all(h);
+    G2.n = nrows;
+    gather_kernel<<<cdiv(nrows, 256), 256, 0, h->stream>>>(G2, h->nbr_off.p, h->slot.p, h->slot_stride, h->walls.n > 0 ? n : 0);
+    h->kernel_launches++;
+  }
+  if (newton_dd) { int rc = dd_reverse(h); if (rc) return rc; }
   CU(cudaGetLastError());
   h->forces_valid = true;
   h->carry = false;   // a snapshot that this pair phase did not consume is stale from here on
@@ -1459,7 +1472,8 @@ int sh_get_stress(const sh_ctx *hc, double virial[9], double kinetic[9]) {
     h->kernel_launches++;
   }
   if (np > 0) {
-    stress_virial_kernel<<<nb_pairs, 256, 0, h->stream>>>(view_all(h), np, n, h->pair_i.p, h->pair_j.p, h->pair_img.p, h->pres.p, h->pres_stride,
+    // newton on: a pair with a ghost is evaluated by one rank only and counts fully there
+    stress_virial_kernel<<<nb_pairs, 256, 0, h->stream>>>(view_all(h), np, h->nrows > n ? (int)h->n : n, h->pair_i.p, h->pair_j.p, h->pair_img.p, h->pres.p, h->pres_stride,
                                                           h->hi[0] - h->lo[0], h->hi[1] - h->lo[1], h->hi[2] - h->lo[2], h->stress_part.p + (size_t)9 * nb_atoms);
     h->kernel_launches++;
   }
@@ -1478,6 +1492,7 @@ int sh_get_ghost_pair_evals(const sh_ctx *hc, int64_t *ghost_pair_evals) {
   CU(cudaStreamSynchronize(h->stream));
   unsigned long long c = 0;
   CU(cudaMemcpy(&c, h->counters.p + 4, sizeof c, cudaMemcpyDeviceToHost));
+  if (h->dd.on && h->dd.newton) c = 0;   // newton on: no pair is evaluated twice
   if (ghost_pair_evals) *ghost_pair_evals = (int64_t)c;
   return 0;
 }
@@ -1588,7 +1603,8 @@ int sh_set_tuning(sh_ctx *h, const char *key, double value) {
     if (!h->shapes.empty()) return fail(h, "cube_n must be set before add_shape");
     if (v != 0 && (v < 8 || v > 144)) return fail(h, "cube_n must be 0 (default) or 8..144");
     h->cube_n = v;
-  } else if (k == "step_trace") { h->step_trace = v != 0; }
+  } else if (k == "newton") { h->dd.newton = v != 0; h->list_valid = false; h->forces_valid = false; }
+  else if (k == "step_trace") { h->step_trace = v != 0; }
   else if (k == "dd_self_ghosts") { h->dd.self_ghosts = v != 0; h->dd.geometry_ok = false; h->dd.borders_ok = false; }
   else if (k == "sync_rebuild") { h->lag_mode = v == 0; h->lag_pending = false; }
   else return fail(h, "unknown tuning key: " + k);

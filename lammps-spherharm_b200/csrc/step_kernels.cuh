@@ -306,7 +306,8 @@ __global__ void wall_kernel(AtomView A, const DevShape *shapes, WallSet W, doubl
 }
 
 // ---- deterministic per-atom accumulation: fixed-order sum of the entry slots ----
-__global__ void gather_kernel(AtomView A, const int *nbr_off, const double *slot, int slot_stride, int use_wall) {
+// nwall: atoms below this index also get their wall force (owned atoms; 0 = no walls)
+__global__ void gather_kernel(AtomView A, const int *nbr_off, const double *slot, int slot_stride, int nwall) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= A.n) return;
   const int st = A.stride;
@@ -316,7 +317,7 @@ __global__ void gather_kernel(AtomView A, const int *nbr_off, const double *slot
 #pragma unroll
     for (int r = 0; r < 6; r++) acc[r] += slot[(size_t)r * slot_stride + e];
   }
-  if (use_wall) {
+  if (i < nwall) {
 #pragma unroll
     for (int r = 0; r < 6; r++) acc[r] += A.wallf[r * st + i];
   }

@@ -33,5 +33,10 @@ def pair_rel_errors(pg, po, rscale=1.0):
         sc = np.maximum(np.linalg.norm(to, axis=1), fn * rscale)
         et = max(et, np.max(np.linalg.norm(tg - to, axis=1) / sc))
     xg, xo = pg["centroid"][ig][m], po["centroid"][io][m]
-    ex = np.max(np.linalg.norm(xg - xo, axis=1)) / rscale
-    return dict(V=eV, F=eF, tau=et, centroid=ex, ncontact=int(m.sum()))
+    dxc = np.linalg.norm(xg - xo, axis=1) / rscale
+    ex = np.max(dxc)
+    # the centroid is a first moment divided by V: for a grazing contact (V -> 0) its rounding error grows like 1/V while
+    # everything it feeds (torques of the dissipative terms) is multiplied by forces ~ V; weight by V / median V
+    Vm = np.median(Vo[m])
+    exw = np.max(dxc * np.minimum(1.0, Vo[m] / Vm))
+    return dict(V=eV, F=eF, tau=et, centroid=ex, centroid_weighted=exw, ncontact=int(m.sum()))

@@ -35,17 +35,20 @@ def _sorted_owned(sim):
     return {k: v[:nl][o] for k, v in st.items()}, info
 
 
-@pytest.mark.parametrize("variant", [0, 16])
-@pytest.mark.parametrize("sync", [0, 1])
-def test_self_ghost_decomposition_equals_periodic_engine(variant, sync):
+@pytest.mark.parametrize("variant,sync,newton", [(0, 0, 1), (16, 0, 1), (16, 1, 0), (0, 1, 0), (16, 0, 0)])
+def test_self_ghost_decomposition_equals_periodic_engine(variant, sync, newton):
+    """newton 1 (default): a pair with a ghost is evaluated once and the reaction returns to the owner (reverse
+    communication); newton 0: both sides evaluate it and keep their own half."""
     cfg = _cfg()
     ref = pkg.ShGpu(); W.apply(ref, cfg); ref.set_pair_tuning(0, 0, variant)
     ref.set_tuning("sync_rebuild", 1)
-    dd = pkg.ShGpu(); dd.set_tuning("dd_self_ghosts", 1); dd.set_tuning("sync_rebuild", sync); dd.dd_init(0, 1)
+    dd = pkg.ShGpu(); dd.set_tuning("dd_self_ghosts", 1); dd.set_tuning("sync_rebuild", sync); dd.set_tuning("newton", newton); dd.dd_init(0, 1)
     W.apply(dd, cfg); dd.set_pair_tuning(0, 0, variant)
     ref.compute_forces(); dd.compute_forces()
     r0 = ref.get_atoms(); d0, info = _sorted_owned(dd)
     assert info["nlocal"] == len(cfg["x"]) and info["nghost"] > 0
+    cr, cd = ref.get_counters()["pair_evals"], dd.get_counters()["pair_evals"]
+    assert (cd == cr) if newton else (cd > cr), (cr, cd)      # newton on: no pair is evaluated twice
     fs = np.abs(r0["f"]).max()
     assert np.abs(d0["f"] - r0["f"]).max() <= 1e-11 * fs
     assert np.abs(d0["torque"] - r0["torque"]).max() <= 1e-11 * fs
