@@ -98,7 +98,7 @@ int sh_dd_get_info(const sh_ctx *h, int pgrid[3], int brick[3], int64_t *nlocal,
                    int64_t *migrated, int64_t *border_builds);
 int sh_get_tags(const sh_ctx *h, int64_t n, int64_t *tags);
 /* per-step device times (ms) of the last sh_run when the "step_trace" knob is on (at most 4096 steps); flags: bit 0 the
- * step rebuilt the neighbor list, bit 1 rebuilt the candidate cache, bit 2 remapped it */
+ * step rebuilt the neighbor list, bit 1 rebuilt the candidate cache, bit 2 remapped it, bit 3 had to grow a device buffer */
 int sh_get_step_trace(const sh_ctx *h, int64_t cap, int64_t *nsteps, double *ms, int *flags);
 /* fix deform xy + remap v (Lees-Edwards shear, BASELINE configs[3]): flow along x, gradient along y, rate = dvx/dy.
  * Before sh_set_atoms; needs a box periodic in x and y; x is never decomposed. */

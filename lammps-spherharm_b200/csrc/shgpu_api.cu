@@ -77,7 +77,9 @@ struct sh_ctx {
   // lagged neighbor decision (sh_run): flag of step s-1 = "step s will exceed the skin"
   int *h_lagflag = nullptr;          // pinned: [0..1] prediction ring, [2] skin violations
   cudaEvent_t ev_lag[2] = {nullptr, nullptr};
-  int lag_slot = 0; bool lag_pending = false, lag_mode = true;
+  int lag_slot = 0; bool lag_pending = false, lag_mode = true, lag_pred_valid = false;
+  bool cache_sync_ranks = false;     // candidate-cache rebuilds are decided from the MAX over ranks of the "nearly used up" flag
+  int64_t step_index = 0, cache_build_step = -10;
   // optional per-step device timeline of the last sh_run ("step_trace" knob)
   bool step_trace = false;
   std::vector<cudaEvent_t> ev_step;
@@ -472,7 +474,9 @@ int absorb_split_feedback(sh_ctx *h) {
   h->last_records = 0;
   for (int s = 0; s < ns; s++) h->last_records += (long long)std::min<unsigned long long>(sc.pool_count[s], (unsigned long long)h->h_pool_cap[s]);
   // hard flag: that phase already ran on the window path; soft flag: rebuild now, while the cache is still valid
-  if ((h->h_cache_invalid[0] != 0 || h->h_cache_invalid[1] != 0) && h->cache_state != CACHE_INVALID) { h->cache_state = CACHE_INVALID; h->cache_exhausted = true; }
+  // (several ranks: the decision comes from the MAX over ranks instead, step_once, so that every rank rebuilds its cache
+  // on the same step and nobody waits for a neighbour's build on top of its own)
+  if (!h->cache_sync_ranks && (h->h_cache_invalid[0] != 0 || h->h_cache_invalid[1] != 0) && h->cache_state != CACHE_INVALID) { h->cache_state = CACHE_INVALID; h->cache_exhausted = true; }
   return 0;
 }
 
@@ -577,7 +581,7 @@ int run_split_pipeline(sh_ctx *h, PairArgs &P) {
       CU(cudaMemsetAsync(h->scalars.p + 3, 0, 2 * sizeof(int), h->stream));
       tock();
       h->kernel_launches++;
-      h->cache_state = CACHE_VALID; h->cache_builds++; h->cache_age = 0; h->cache_epoch = h->atoms_epoch;
+      h->cache_state = CACHE_VALID; h->cache_builds++; h->cache_age = 0; h->cache_epoch = h->atoms_epoch; h->cache_build_step = h->step_index;
     } else {
       if ((rc = check_validity())) return rc;
     }
@@ -1128,11 +1132,15 @@ int step_once(sh_ctx *h) {
   bool decided = false;
   if (!due) decided = true;
   else if (!h->neigh_check) { rebuild = 1; decided = true; }
+  h->step_index++;
+  h->cache_sync_ranks = lag && dd && h->dd.nranks > 1;
   if (lag && h->lag_pending) {   // no prediction in flight (first step, or the step after a rebuild): classic decision below
     CU(cudaEventSynchronize(h->ev_lag[h->lag_slot]));
-    const int pred = h->h_lagflag[h->lag_slot];
+    const int soft = h->h_lagflag[4 + 2 * h->lag_slot], pred = h->h_lagflag[5 + 2 * h->lag_slot];
     h->lag_pending = false;
-    if (!decided) { rebuild = pred; decided = true; }
+    if (!decided && h->lag_pred_valid) { rebuild = pred; decided = true; }
+    // cache request of ANY rank, as of two pair phases ago; the flags a cache build resets are stale for one more step
+    if (h->cache_sync_ranks && soft && h->cache_state == CACHE_VALID && h->step_index > h->cache_build_step + 2) { h->cache_state = CACHE_INVALID; h->cache_exhausted = true; }
   }
   if ((rc = launch_integrate_initial(h, decided && !rebuild))) return rc;
   if (!decided) {   // classic decision: this step's own displacement flag, one host round trip
@@ -1142,12 +1150,15 @@ int step_once(sh_ctx *h) {
     rebuild = h->h_pinned[4] != 0;
   }
   if (lag) {
-    if (!rebuild) {   // a prediction made on a rebuild step refers to the old origins: dropped
-      if ((rc = reduce_flag(h, h->scalars.p + 5))) return rc;
+    // sc[4] (cache nearly used up, sticky until the cache is rebuilt) and sc[5] (prediction) -> MAX over ranks in sc[10..11]
+    if (h->cache_sync_ranks || !rebuild) {
+      if (dd && h->dd.nranks > 1) NC(h->dd.nccl->AllReduce(h->scalars.p + 4, h->scalars.p + 10, 2, ncclInt, ncclMax, h->dd.comm, h->stream));
+      else CU(cudaMemcpyAsync(h->scalars.p + 10, h->scalars.p + 4, 2 * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
       h->lag_slot ^= 1;
-      CU(cudaMemcpyAsync(h->h_lagflag + h->lag_slot, h->scalars.p + 5, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaMemcpyAsync(h->h_lagflag + 4 + 2 * h->lag_slot, h->scalars.p + 10, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
       CU(cudaEventRecord(h->ev_lag[h->lag_slot], h->stream));
       h->lag_pending = true;
+      h->lag_pred_valid = !rebuild;   // a prediction made on a rebuild step refers to the old origins: dropped
     }
     CU(cudaMemsetAsync(h->scalars.p + 5, 0, sizeof(int), h->stream));
   }
@@ -1205,10 +1216,12 @@ int sh_run(sh_ctx *h, int64_t nsteps) {
   }
   for (int64_t step = 0; step < nsteps; step++) {
     const int64_t nb0 = h->neighbor_builds, cb0 = h->cache_builds, cr0 = h->cache_remaps;
+    const long long al0 = devbuf_stats().allocs;
     if ((rc = step_once(h))) return rc;
     if (trace) {
       CU(cudaEventRecord(h->ev_step[step + 1], h->stream));
-      h->step_flags[step] = (h->neighbor_builds > nb0 ? 1 : 0) | (h->cache_builds > cb0 ? 2 : 0) | (h->cache_remaps > cr0 ? 4 : 0);
+      h->step_flags[step] = (h->neighbor_builds > nb0 ? 1 : 0) | (h->cache_builds > cb0 ? 2 : 0) | (h->cache_remaps > cr0 ? 4 : 0) |
+                            (devbuf_stats().allocs > al0 ? 8 : 0);
     }
   }
   CU(cudaMemcpyAsync(h->h_lagflag + 2, h->scalars.p + 6, sizeof(int), cudaMemcpyDeviceToHost, h->stream));

@@ -114,7 +114,7 @@ __global__ void cache_check_kernel(AtomView A, const DevShape *shapes, int level
   const double ang = dq < 0.2 ? 2.02 * dq : 10.0;       // angle <= 2.02 dq for small rotations
   const double w = sqrt(u2) + ang * (s.rmax + s.cache_delta[level]);
   if (!(w <= thresh)) flag[0] = 1;            // margin used up: the cached cull stands down this step
-  else if (!(w <= 0.75 * thresh)) flag[1] = 1;  // nearly used up: the host rebuilds the cache before the next phase
+  if (!(w <= 0.75 * thresh)) flag[1] = 1;     // (nearly) used up: the host rebuilds the cache before a later phase
 }
 __global__ void cache_origin_kernel(AtomView A) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

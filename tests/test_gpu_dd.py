@@ -22,7 +22,7 @@ pytestmark = pytest.mark.gpu
 
 def _cfg():
     cfg = W.packing((6, 4, 4), 20, (32, 64), nshapes=4, seed=21, periodic=True, name="dd", skin=0.03, vel_sigma=0.5, dt=4e-4)
-    cfg["v"] = cfg["v"] + np.array([2.0, 1.0, 0.0])      # a drift, so that atoms cross brick / box boundaries (migration)
+    cfg["v"] = cfg["v"] + np.array([8.0, 1.0, 0.0])      # a drift, so that atoms cross brick / box boundaries (migration)
     return cfg
 
 
@@ -94,7 +94,7 @@ local = int(os.environ["LOCAL_RANK"]); torch.cuda.set_device(local)
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 cfg = W.packing((6, 4, 4), 20, (32, 64), nshapes=4, seed=21, periodic=True, name="mr", skin=0.03, vel_sigma=0.5, dt=4e-4)
-cfg["v"] = cfg["v"] + np.array([2.0, 1.0, 0.0])      # a drift, so that atoms cross the brick boundaries (migration)
+cfg["v"] = cfg["v"] + np.array([8.0, 1.0, 0.0])      # a drift, so that atoms cross the brick boundaries (migration)
 nsteps = 300
 for variant in (16, 0):
     sim = D.native_engine(pkg, cfg, local)
