@@ -507,7 +507,11 @@ def strong_case(args, pkg, torch, dist, use_dist, local, world, rank, allsum):
     """BASELINE configs[3] size: 1,008,000 particles (6x6x7 unit cells), fixed TOTAL size on the N GPUs of this run."""
     import copy
     a = copy.copy(args)
+    a.flow = 0.0
     cfg = make_workload(a, pkg, 1008000)
+    lo, hi, _ = cfg["box"]
+    rate = args.shear_velocity / float(hi[1] - lo[1])       # Lees-Edwards: the box top moves at shear_velocity relative to the bottom
+    cfg = pkg.workloads.shear_box(cfg, rate)
     run = Runner(pkg, cfg, local, world)
     run.setup()
     run.block(3)
@@ -519,12 +523,16 @@ def strong_case(args, pkg, torch, dist, use_dist, local, world, rank, allsum):
     steps_timed = len(times) * a.steps
     pairs_total, nb = allsum([pairs_local, cnt["neighbor_builds"]])
     med = float(np.median(times)) / a.steps
+    info = run.sim.dd_info()
     run.close()
     if rank != 0:
         return None
     out = {"n_particles": len(cfg["x"]), "n_gpus": world, "ms_per_step": 1e3 * med, "value": pairs_total / steps_timed / med, "unit": UNIT,
            "steps_timed": steps_timed, "neighbor_builds": int(nb), "scaling": "strong",
-           "workload": "the bench packing tiled 6x6x7 (1,008,000 particles), same flow, periodic box (no Lees-Edwards shear)"}
+           "shear_rate": rate, "decomposition": "x".join(str(v) for v in info["pgrid"]), "ghosts_per_rank": info["nghost"],
+           "workload": "BASELINE configs[3]: the bench packing tiled 6x6x7 (1,008,000 particles) as a periodic SHEAR box: Lees-Edwards "
+                       "images (sh_set_shear; flow x, gradient y, linear velocity profile, box top moving at %g relative to the bottom) "
+                       "+ thermal %g; neighbor and cache rebuilds inside the timed region" % (args.shear_velocity, args.vel_sigma)}
     path = os.path.join(ROOT, "gpurun_out", "strong_1M_n1.json")
     if world == 1:
         try:
@@ -563,6 +571,7 @@ def main():
     ap.add_argument("--ntheta", type=int, default=48)
     ap.add_argument("--nphi", type=int, default=96)
     ap.add_argument("--flow", type=float, default=15.0, help="bulk flow velocity along x (granular pour)")
+    ap.add_argument("--shear-velocity", type=float, default=15.0, help="strong_1M case: velocity of the box top relative to the bottom")
     ap.add_argument("--vel-sigma", type=float, default=0.02, help="thermal velocity on top of the flow")
     ap.add_argument("--strong", action="store_true", help="N>1: keep the TOTAL particle count at --particles (strong scaling)")
     ap.add_argument("--no-cpu", action="store_true")

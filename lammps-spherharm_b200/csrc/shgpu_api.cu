@@ -531,10 +531,12 @@ int run_split_pipeline(sh_ctx *h, PairArgs &P) {
       if (h->carry) {   // decomposed rebuild: find every new atom among the old ones, carry its cache reference state over
         try { h->amap.ensure((size_t)h->n + 2); } catch (std::string &e) { return fail(h, e); }
         const int nstay = h->dd.last_nstay, nown = (int)(h->n - h->nghost);
+        CU(cudaMemsetAsync(h->drift.p + 4, 0, 4 * sizeof(double), h->stream));
         dd_cache_map_kernel<<<cdiv(h->n, 256), 256, 0, h->stream>>>(view_all(h), h->d_tag.p, nown, nstay, h->dd.order.p, h->old_tag.p, h->old_c.p,
                                                                     h->old_stride, h->old_nown, h->old_n, h->ghost_hash.p, h->ghost_hash_size,
-                                                                    0.25 * h->dd.G.rc * h->dd.G.rc, h->old_cc0.p, h->old_cq0.p, h->amap.p);
-        h->kernel_launches++;
+                                                                    0.25 * h->dd.G.rc * h->dd.G.rc, h->old_cc0.p, h->old_cq0.p, h->amap.p, h->drift.p + 4);
+        dd_cache_new_atoms_kernel<<<cdiv(h->n, 256), 256, 0, h->stream>>>(view_all(h), h->amap.p, h->drift.p + 4);
+        h->kernel_launches += 2;
         amap = h->amap.p;
         h->carry = false; h->cache_epoch = h->atoms_epoch;
       }
@@ -803,7 +805,7 @@ int sh_create(sh_ctx **out, int device_id) {
   h->pm.assign(SH_MAX_SHAPES * SH_MAX_SHAPES, 1.0);
   h->pgn.assign(SH_MAX_SHAPES * SH_MAX_SHAPES, 0.0); h->pgt.assign(SH_MAX_SHAPES * SH_MAX_SHAPES, 0.0); h->pmu.assign(SH_MAX_SHAPES * SH_MAX_SHAPES, 0.0);
   try {
-    h->scalars.ensure(16); h->bbox.ensure(8); h->counters.ensure(16); h->drift.ensure(4);
+    h->scalars.ensure(16); h->bbox.ensure(8); h->counters.ensure(16); h->drift.ensure(8);
   } catch (std::string &) { delete h; return -7; }
   cudaMemset(h->scalars.p, 0, 16 * sizeof(int));
   cudaMemset(h->counters.p, 0, 16 * sizeof(unsigned long long));
