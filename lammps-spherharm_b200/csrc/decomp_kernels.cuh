@@ -249,7 +249,8 @@ __global__ void dd_ghost_hash_kernel(const long long *old_tag, int nown, int ngh
 // quaternion at the last cache build) follows the atom; a new atom starts from its current state.
 __global__ void dd_cache_map_kernel(AtomView A, const long long *tag, int nown, int nstay, const int *order, const long long *old_tag,
                                     const double *old_c, int old_stride, int old_nown, int old_n, const int *table, int hs, double near2,
-                                    const double *old_cc0, const double *old_cq0, int *amap, double *acc /* 4: sum of c - cc0 over the matched atoms, count */) {
+                                    const double *old_cc0, const double *old_cq0, int *amap, double Ly, double le_doff, double pc0, double pc1,
+                                    double pc2, double *acc /* CACHE_FIT_N sums over the matched atoms */) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = a < A.n;
   const int st = A.stride;
@@ -275,29 +276,39 @@ __global__ void dd_cache_map_kernel(AtomView A, const long long *tag, int nown, 
     // box vector since the snapshot, which was taken from the same positions before the wrap: the reference origin jumps
     // with it, or the cache would read the jump as a displacement and be rebuilt at every neighbor rebuild of a flow
 #pragma unroll
-    for (int d = 0; d < 3; d++) {
-      const double jump = a < nown ? A.c[d * st + a] - old_c[d * old_stride + o] : 0.0;
-      A.cc0[d * st + a] = old_cc0[d * old_stride + o] + jump;
+    // Under Lees-Edwards shear an atom that crossed y continues as its own image, whose reference position also carries
+    // the image offset AT THE TIME THE CACHE WAS BUILT: x gains ny * (offset now - offset then) on top of the jump.
+    double jump[3] = {0, 0, 0};
+    if (a < nown) {
+#pragma unroll
+      for (int d = 0; d < 3; d++) jump[d] = A.c[d * st + a] - old_c[d * old_stride + o];
+      if (le_doff != 0.0) jump[0] += rint(-jump[1] / Ly) * le_doff;
     }
+#pragma unroll
+    for (int d = 0; d < 3; d++) A.cc0[d * st + a] = old_cc0[d * old_stride + o] + jump[d];
 #pragma unroll
     for (int d = 0; d < 4; d++) A.cq0[d * st + a] = old_cq0[d * old_stride + o];
   }
-  // mean displacement of the atoms that were already here (the bulk motion since the cache was built)
-  double d0 = 0, d1 = 0, d2 = 0, one = 0;
-  if (o >= 0) { d0 = A.c[a] - A.cc0[a]; d1 = A.c[st + a] - A.cc0[st + a]; d2 = A.c[2 * st + a] - A.cc0[2 * st + a]; one = 1.0; }
-  d0 = warp_sum(d0); d1 = warp_sum(d1); d2 = warp_sum(d2); one = warp_sum(one);
-  if ((threadIdx.x & 31) == 0 && one > 0) { atomicAdd(&acc[0], d0); atomicAdd(&acc[1], d1); atomicAdd(&acc[2], d2); atomicAdd(&acc[3], one); }
+  // affine displacement field of the atoms that were already here (the bulk motion / shear since the cache was built)
+  double p[3] = {0, 0, 0}, dd[3] = {0, 0, 0};
+  if (o >= 0) {
+#pragma unroll
+    for (int d = 0; d < 3; d++) { p[d] = A.cc0[d * st + a]; dd[d] = A.c[d * st + a] - p[d]; }
+  }
+  const double pc[3] = {pc0, pc1, pc2};
+  cache_fit_accumulate(o >= 0, p, dd, pc, acc);
 }
 // an atom that is new on this rank starts from its current state, placed where the bulk motion would have taken it from:
-// its reference origin is the current one minus the mean displacement of the others (cache_check_kernel measures every
-// atom against that mean), its reference quaternion the current one
-__global__ void dd_cache_new_atoms_kernel(AtomView A, const int *amap, const double *acc) {
+// its reference origin is the current one minus the affine displacement field of the others at its position
+// (cache_check_kernel measures every atom against that field), its reference quaternion the current one
+__global__ void dd_cache_new_atoms_kernel(AtomView A, const int *amap, const double *fit, double pc0, double pc1, double pc2) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= A.n || amap[a] >= 0) return;
   const int st = A.stride;
-  const double inv = acc[3] > 0 ? 1.0 / acc[3] : 0.0;
+  const double q[3] = {(A.c[a] - pc0) - fit[3], (A.c[st + a] - pc1) - fit[4], (A.c[2 * st + a] - pc2) - fit[5]};
 #pragma unroll
-  for (int d = 0; d < 3; d++) A.cc0[d * st + a] = A.c[d * st + a] - acc[d] * inv;
+  for (int d = 0; d < 3; d++)
+    A.cc0[d * st + a] = A.c[d * st + a] - (fit[d] + (fit[6 + 3 * d] * q[0] + fit[7 + 3 * d] * q[1] + fit[8 + 3 * d] * q[2]));
 #pragma unroll
   for (int d = 0; d < 4; d++) A.cq0[d * st + a] = A.q[d * st + a];
 }

@@ -80,6 +80,7 @@ struct sh_ctx {
   int lag_slot = 0; bool lag_pending = false, lag_mode = true, lag_pred_valid = false;
   bool cache_sync_ranks = false;     // candidate-cache rebuilds are decided from the MAX over ranks of the "nearly used up" flag
   int64_t step_index = 0, cache_build_step = -10;
+  double cache_time = 0.0;           // simulation time of the last full cache build (Lees-Edwards offset then)
   // optional per-step device timeline of the last sh_run ("step_trace" knob)
   bool step_trace = false;
   std::vector<cudaEvent_t> ev_step;
@@ -511,14 +512,21 @@ int run_split_pipeline(sh_ctx *h, PairArgs &P) {
     const int cur = h->cache_cur;
     try { h->cache_hot[cur].ensure((size_t)np + 2); h->cache_count.ensure(2); h->fresh_list.ensure((size_t)np + 2); }
     catch (std::string &e) { return fail(h, e); }
+    // origin of the moment sums of the displacement fit: the box centre (finite boxes) keeps them well conditioned
+    double pc[3];
+    for (int d = 0; d < 3; d++) pc[d] = (h->hi[d] < 1e29 && h->lo[d] > -1e29) ? 0.5 * (h->lo[d] + h->hi[d]) : 0.0;
     auto check_validity = [&]() -> int {   // raises the device flag scalars[3] when a particle used up its margin
       double dmin = 1e300;
       for (auto &sh : h->shapes) dmin = std::min(dmin, sh.cache_delta[h->cache_level]);
-      CU(cudaMemsetAsync(h->drift.p, 0, 3 * sizeof(double), h->stream));
-      cache_drift_kernel<<<cdiv(h->n, 256), 256, 0, h->stream>>>(view_all(h), h->drift.p);
-      cache_check_kernel<<<cdiv(h->n, 256), 256, 0, h->stream>>>(view_all(h), h->d_shapes.p, h->cache_level, 0.5 * dmin, h->drift.p,
-                                                                 1.0 / (double)h->n, h->scalars.p + 3);
-      h->kernel_launches += 2;
+      double rmaxg = 0;
+      for (auto &sh : h->shapes) rmaxg = std::max(rmaxg, sh.rmax);
+      const double rpair = 2.0 * rmaxg + 2.0 * h->skin;   // no pair of the list is further apart than this
+      CU(cudaMemsetAsync(h->drift.p, 0, CACHE_FIT_N * sizeof(double), h->stream));
+      cache_drift_kernel<<<cdiv(h->n, 256), 256, 0, h->stream>>>(view_all(h), pc[0], pc[1], pc[2], h->drift.p);
+      cache_fit_solve_kernel<<<1, 32, 0, h->stream>>>(h->drift.p, h->drift.p + 32);
+      cache_check_kernel<<<cdiv(h->n, 256), 256, 0, h->stream>>>(view_all(h), h->d_shapes.p, h->cache_level, 0.5 * dmin, h->drift.p + 32,
+                                                                 pc[0], pc[1], pc[2], rpair, h->scalars.p + 3);
+      h->kernel_launches += 3;
       return 0;
     };
     if (h->cache_state == CACHE_REMAP && h->cache_level + 1 < SH_CACHE_LEVELS && !(h->tune_variant & 32)) {
@@ -531,12 +539,15 @@ int run_split_pipeline(sh_ctx *h, PairArgs &P) {
       if (h->carry) {   // decomposed rebuild: find every new atom among the old ones, carry its cache reference state over
         try { h->amap.ensure((size_t)h->n + 2); } catch (std::string &e) { return fail(h, e); }
         const int nstay = h->dd.last_nstay, nown = (int)(h->n - h->nghost);
-        CU(cudaMemsetAsync(h->drift.p + 4, 0, 4 * sizeof(double), h->stream));
+        CU(cudaMemsetAsync(h->drift.p + 64, 0, CACHE_FIT_N * sizeof(double), h->stream));
+        const double le_doff = h->dd.le_rate * h->dd.glen[1] * (h->time - h->cache_time);
         dd_cache_map_kernel<<<cdiv(h->n, 256), 256, 0, h->stream>>>(view_all(h), h->d_tag.p, nown, nstay, h->dd.order.p, h->old_tag.p, h->old_c.p,
                                                                     h->old_stride, h->old_nown, h->old_n, h->ghost_hash.p, h->ghost_hash_size,
-                                                                    0.25 * h->dd.G.rc * h->dd.G.rc, h->old_cc0.p, h->old_cq0.p, h->amap.p, h->drift.p + 4);
-        dd_cache_new_atoms_kernel<<<cdiv(h->n, 256), 256, 0, h->stream>>>(view_all(h), h->amap.p, h->drift.p + 4);
-        h->kernel_launches += 2;
+                                                                    0.25 * h->dd.G.rc * h->dd.G.rc, h->old_cc0.p, h->old_cq0.p, h->amap.p, h->dd.glen[1], le_doff,
+                                                                    pc[0], pc[1], pc[2], h->drift.p + 64);
+        cache_fit_solve_kernel<<<1, 32, 0, h->stream>>>(h->drift.p + 64, h->drift.p + 96);
+        dd_cache_new_atoms_kernel<<<cdiv(h->n, 256), 256, 0, h->stream>>>(view_all(h), h->amap.p, h->drift.p + 96, pc[0], pc[1], pc[2]);
+        h->kernel_launches += 3;
         amap = h->amap.p;
         h->carry = false; h->cache_epoch = h->atoms_epoch;
       }
@@ -584,6 +595,7 @@ int run_split_pipeline(sh_ctx *h, PairArgs &P) {
       tock();
       h->kernel_launches++;
       h->cache_state = CACHE_VALID; h->cache_builds++; h->cache_age = 0; h->cache_epoch = h->atoms_epoch; h->cache_build_step = h->step_index;
+      h->cache_time = h->time;
     } else {
       if ((rc = check_validity())) return rc;
     }
@@ -805,7 +817,7 @@ int sh_create(sh_ctx **out, int device_id) {
   h->pm.assign(SH_MAX_SHAPES * SH_MAX_SHAPES, 1.0);
   h->pgn.assign(SH_MAX_SHAPES * SH_MAX_SHAPES, 0.0); h->pgt.assign(SH_MAX_SHAPES * SH_MAX_SHAPES, 0.0); h->pmu.assign(SH_MAX_SHAPES * SH_MAX_SHAPES, 0.0);
   try {
-    h->scalars.ensure(16); h->bbox.ensure(8); h->counters.ensure(16); h->drift.ensure(8);
+    h->scalars.ensure(16); h->bbox.ensure(8); h->counters.ensure(16); h->drift.ensure(128);
   } catch (std::string &) { delete h; return -7; }
   cudaMemset(h->scalars.p, 0, 16 * sizeof(int));
   cudaMemset(h->counters.p, 0, 16 * sizeof(unsigned long long));

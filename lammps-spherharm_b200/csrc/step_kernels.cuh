@@ -84,35 +84,109 @@ __global__ void unpack_atoms_kernel(AtomView A, int first, int m, const double *
 }
 
 // candidate cache (pair_split_kernels.cuh): what matters is how far a node of atom a has moved RELATIVE to its partner b.
-// For any common vector u:  |dc_a - dc_b| <= |dc_a - u| + |dc_b - u|, so with u = the mean displacement of all atoms
-// since the cache was built (a bulk flow moves every atom but no pair) a node of atom i has moved, relative to any
-// partner frame, by at most  w_i = |dc_i - u| + angle(q0 -> q) * (rmax_i + delta_i); the cache stays valid while every
-// w_i <= thresh.  u only steers WHEN the cache is rebuilt, never a force: its (atomic, order-dependent) sum is harmless.
-__global__ void cache_drift_kernel(AtomView A, double *acc /* 3: sum of c - cc0 */) {
+// For any common displacement field u(x):  |dc_a - dc_b| <= |dc_a - u(p_a)| + |dc_b - u(p_b)| + |u(p_a) - u(p_b)|.  With u the
+// least-squares AFFINE field  u(p) = dbar + G (p - pbar)  over all atoms (p = SH origin when the cache was built,
+// dc = displacement since) a bulk flow (G = 0) moves no pair and a shear or compression only by |G| x the pair distance:
+// a node of atom i has moved, relative to any partner frame, by at most
+//   w_i = |dc_i - u(p_i)| + angle(q0 -> q) * (rmax_i + delta_i) + |G|_F * rpair / 2,
+// and the cache stays valid while every w_i <= thresh.  The fit only steers WHEN the cache is rebuilt, never a force: its
+// (atomic, order-dependent) sums are harmless.
+// acc: [0] count, [1..3] sum p, [4..6] sum d, [7..12] sum p (x) p (xx xy xz yy yz zz), [13..21] sum d (x) p (row d)
+#define CACHE_FIT_N 22
+__device__ __forceinline__ void cache_fit_accumulate(bool use, const double p[3], const double d[3], const double pc[3], double *acc) {
+  __shared__ double s_fit[8][CACHE_FIT_N];
+  double v[CACHE_FIT_N];
+#pragma unroll
+  for (int k = 0; k < CACHE_FIT_N; k++) v[k] = 0.0;
+  if (use) {
+    const double q[3] = {p[0] - pc[0], p[1] - pc[1], p[2] - pc[2]};
+    v[0] = 1.0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { v[1 + k] = q[k]; v[4 + k] = d[k]; }
+    v[7] = q[0] * q[0]; v[8] = q[0] * q[1]; v[9] = q[0] * q[2]; v[10] = q[1] * q[1]; v[11] = q[1] * q[2]; v[12] = q[2] * q[2];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) v[13 + 3 * r + k] = d[r] * q[k];
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < CACHE_FIT_N; k++) v[k] = warp_sum(v[k]);
+  if (lane == 0) for (int k = 0; k < CACHE_FIT_N; k++) s_fit[warp][k] = v[k];
+  __syncthreads();
+  if (threadIdx.x < CACHE_FIT_N) {
+    double t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += s_fit[w][threadIdx.x];
+    if (t != 0.0) atomicAdd(&acc[threadIdx.x], t);
+  }
+}
+__global__ void cache_drift_kernel(AtomView A, double pc0, double pc1, double pc2, double *acc) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int st = A.stride;
-  double d0 = 0, d1 = 0, d2 = 0;
-  if (i < A.n) { d0 = A.c[i] - A.cc0[i]; d1 = A.c[st + i] - A.cc0[st + i]; d2 = A.c[2 * st + i] - A.cc0[2 * st + i]; }
-  d0 = warp_sum(d0); d1 = warp_sum(d1); d2 = warp_sum(d2);
-  if ((threadIdx.x & 31) == 0) { atomicAdd(&acc[0], d0); atomicAdd(&acc[1], d1); atomicAdd(&acc[2], d2); }
+  const bool use = i < A.n;
+  double p[3] = {0, 0, 0}, d[3] = {0, 0, 0};
+  if (use) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) { p[k] = A.cc0[k * st + i]; d[k] = A.c[k * st + i] - p[k]; }
+  }
+  const double pc[3] = {pc0, pc1, pc2};
+  cache_fit_accumulate(use, p, d, pc, acc);
 }
-__global__ void cache_check_kernel(AtomView A, const DevShape *shapes, int level, double thresh, const double *acc, double inv_n,
-                                   int *flag) {
+// fit[0..2] dbar, [3..5] pbar (relative to pc), [6..14] G (row-major), [15] |G|_F
+__global__ void cache_fit_solve_kernel(const double *acc, double *fit) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double n = acc[0];
+  for (int k = 0; k < 16; k++) fit[k] = 0.0;
+  if (!(n > 0)) return;
+  const double inv = 1.0 / n;
+  double pb[3], db[3];
+  for (int k = 0; k < 3; k++) { pb[k] = acc[1 + k] * inv; db[k] = acc[4 + k] * inv; fit[k] = db[k]; fit[3 + k] = pb[k]; }
+  if (n < 16) return;
+  const double C[3][3] = {{acc[7] * inv - pb[0] * pb[0], acc[8] * inv - pb[0] * pb[1], acc[9] * inv - pb[0] * pb[2]},
+                          {acc[8] * inv - pb[1] * pb[0], acc[10] * inv - pb[1] * pb[1], acc[11] * inv - pb[1] * pb[2]},
+                          {acc[9] * inv - pb[2] * pb[0], acc[11] * inv - pb[2] * pb[1], acc[12] * inv - pb[2] * pb[2]}};
+  double B[3][3];
+  for (int r = 0; r < 3; r++) for (int k = 0; k < 3; k++) B[r][k] = acc[13 + 3 * r + k] * inv - db[r] * pb[k];
+  const double det = C[0][0] * (C[1][1] * C[2][2] - C[1][2] * C[2][1]) - C[0][1] * (C[1][0] * C[2][2] - C[1][2] * C[2][0]) +
+                     C[0][2] * (C[1][0] * C[2][1] - C[1][1] * C[2][0]);
+  const double tr = C[0][0] + C[1][1] + C[2][2];
+  if (!(det > 1e-9 * tr * tr * tr) || !(tr > 0)) return;   // atoms (nearly) in a plane or on a line: plain mean only
+  const double id = 1.0 / det;
+  const double Ci[3][3] = {{(C[1][1] * C[2][2] - C[1][2] * C[2][1]) * id, (C[0][2] * C[2][1] - C[0][1] * C[2][2]) * id, (C[0][1] * C[1][2] - C[0][2] * C[1][1]) * id},
+                           {(C[1][2] * C[2][0] - C[1][0] * C[2][2]) * id, (C[0][0] * C[2][2] - C[0][2] * C[2][0]) * id, (C[0][2] * C[1][0] - C[0][0] * C[1][2]) * id},
+                           {(C[1][0] * C[2][1] - C[1][1] * C[2][0]) * id, (C[0][1] * C[2][0] - C[0][0] * C[2][1]) * id, (C[0][0] * C[1][1] - C[0][1] * C[1][0]) * id}};
+  double g2 = 0;
+  for (int r = 0; r < 3; r++)
+    for (int k = 0; k < 3; k++) {
+      const double g = B[r][0] * Ci[0][k] + B[r][1] * Ci[1][k] + B[r][2] * Ci[2][k];
+      fit[6 + 3 * r + k] = g; g2 += g * g;
+    }
+  fit[15] = sqrt(g2);
+}
+__global__ void cache_check_kernel(AtomView A, const DevShape *shapes, int level, double thresh, const double *fit, double pc0, double pc1,
+                                   double pc2, double rpair, int *flag) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= A.n) return;
   const int st = A.stride;
   const DevShape &s = shapes[A.shape[i]];
+  const double pc[3] = {pc0, pc1, pc2};
+  double q[3], d[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) { const double p = A.cc0[k * st + i]; q[k] = (p - pc[k]) - fit[3 + k]; d[k] = A.c[k * st + i] - p; }
   double u2 = 0, dm = 0, dp = 0;
 #pragma unroll
-  for (int d = 0; d < 3; d++) { const double dd = (A.c[d * st + i] - A.cc0[d * st + i]) - acc[d] * inv_n; u2 += dd * dd; }
+  for (int r = 0; r < 3; r++) {
+    const double dd = d[r] - fit[r] - (fit[6 + 3 * r] * q[0] + fit[7 + 3 * r] * q[1] + fit[8 + 3 * r] * q[2]);
+    u2 += dd * dd;
+  }
 #pragma unroll
-  for (int d = 0; d < 4; d++) {
-    const double a = A.q[d * st + i], b = A.cq0[d * st + i];
+  for (int k = 0; k < 4; k++) {
+    const double a = A.q[k * st + i], b = A.cq0[k * st + i];
     dm += (a - b) * (a - b); dp += (a + b) * (a + b);
   }
   const double dq = sqrt(fmin(dm, dp));                 // = 2 sin(angle/4)
   const double ang = dq < 0.2 ? 2.02 * dq : 10.0;       // angle <= 2.02 dq for small rotations
-  const double w = sqrt(u2) + ang * (s.rmax + s.cache_delta[level]);
+  const double w = sqrt(u2) + ang * (s.rmax + s.cache_delta[level]) + 0.5 * fit[15] * rpair;
   if (!(w <= thresh)) flag[0] = 1;            // margin used up: the cached cull stands down this step
   if (!(w <= 0.75 * thresh)) flag[1] = 1;     // (nearly) used up: the host rebuilds the cache before a later phase
 }

