@@ -496,6 +496,8 @@ def run_graft(args):
         if mgc is not None:
             line["multi_gpu_check"] = mgc
         line["migrated_atoms_per_rank"] = dd_info["migrated"]
+        line["comm_ms_per_step"] = 1e3 * tim["seconds_other"] / steps_timed   # rank 0: exchange sections incl. waiting for neighbours
+        line["ghosts_per_rank"] = dd_info["nghost"]
         if cpu:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
     if use_dist:
@@ -524,11 +526,16 @@ def strong_case(args, pkg, torch, dist, use_dist, local, world, rank, allsum):
     pairs_total, nb = allsum([pairs_local, cnt["neighbor_builds"]])
     med = float(np.median(times)) / a.steps
     info = run.sim.dd_info()
+    tim = run.sim.get_timers()
+    spl = run.sim.get_split_times()
     run.close()
     if rank != 0:
         return None
     out = {"n_particles": len(cfg["x"]), "n_gpus": world, "ms_per_step": 1e3 * med, "value": pairs_total / steps_timed / med, "unit": UNIT,
            "steps_timed": steps_timed, "neighbor_builds": int(nb), "scaling": "strong",
+           "mean_ms_per_step": 1e3 * sum(times) / steps_timed, "pair_ms_per_step": 1e3 * tim["seconds_pair"] / steps_timed,
+           "comm_ms_per_step": 1e3 * tim["seconds_other"] / steps_timed, "neigh_ms_per_step": 1e3 * tim["seconds_neigh"] / steps_timed,
+           "kernel_ms_per_step": {k: 1e3 * v / steps_timed for k, v in spl.items()},
            "shear_rate": rate, "decomposition": "x".join(str(v) for v in info["pgrid"]), "ghosts_per_rank": info["nghost"],
            "workload": "BASELINE configs[3]: the bench packing tiled 6x6x7 (1,008,000 particles) as a periodic SHEAR box: Lees-Edwards "
                        "images (sh_set_shear; flow x, gradient y, linear velocity profile, box top moving at %g relative to the bottom) "

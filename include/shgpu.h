@@ -133,7 +133,9 @@ int sh_get_counters(const sh_ctx *h, int64_t *pair_evals, int64_t *nodes_transfo
                     int64_t *kernel_launches);
 /* pair evaluations whose second atom is a ghost (each such pair is also evaluated by the owner rank) */
 int sh_get_ghost_pair_evals(const sh_ctx *h, int64_t *ghost_pair_evals);
-/* device time (CUDA events on the library's stream) accumulated since sh_reset_timers ---------- */
+/* device time (CUDA events on the library's stream) accumulated since sh_reset_timers; seconds_other = the decomposition's
+ * communication sections (pack + NCCL + unpack of the ghost exchange and the force return, migration + borders), which
+ * include the time spent waiting for slower neighbour ranks ---------- */
 int sh_get_timers(const sh_ctx *h, double *seconds_pair, int64_t *pair_launches,
                   double *seconds_neigh, double *seconds_other);
 int sh_reset_timers(sh_ctx *h);

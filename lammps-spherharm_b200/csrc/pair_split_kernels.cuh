@@ -39,14 +39,18 @@ struct __align__(16) SurvRec {
 
 // one run of records per (pair, direction).  Nodes that the cull already proved inside (inscribed sphere / per-cell lower
 // bound) need no evaluation: up to 7 of them are kept inline here instead of occupying lanes of pair_eval_kernel.
+// Further proven-inside nodes go to a separate index pool (`inpool`, 4 B per node) that pair_eval_kernel never sees: a deep
+// overlap on a fine quadrature (80x160 nodes) has dozens of them per pair.
 struct __align__(16) PdEntry {
   long long off;            // first record of the run (absolute index into the pool)
   int cnt;                  // records in the run; -1 = the pair is on the deep-contact list
-  int ntrans;               // candidate nodes the cull transformed for this direction (counter [1])
+  unsigned short ntrans;    // candidate nodes the cull transformed for this direction (counter [1])
+  unsigned short cnt2;      // proven-inside nodes of this direction in the index pool
+  unsigned int off2;        // ... starting here
   unsigned short nin;       // inline inside nodes
-  unsigned short in[7];
+  unsigned short in[5];
 };
-#define PD_INLINE 7
+#define PD_INLINE 5
 
 // everything the cached cull needs to start a pair, in one 32 B sector (written by the cache build)
 struct __align__(16) PairHot {
@@ -65,6 +69,7 @@ struct EvalPlanDev {
 // per-step device scalars of the split pipeline (zeroed by one memset at the start of the pair phase)
 struct SplitScalars {
   unsigned long long pool_count[SH_MAX_SHAPES];   // records appended this step (may exceed cap -> host grows the pool)
+  unsigned long long in_count;                    // entries appended to the inside-node index pool (same rule)
   int nbig;            // pairs on the deep-contact list
   int nslow;           // pairs without a cache entry
   int slow_counter;    // work counter of the window kernel
@@ -80,6 +85,8 @@ struct SplitArgs {
   PdEntry *pd;                    // [2P] record run + inline inside nodes per (pair, direction)
   int *big_list;                  // [P]
   int *slow_list;                 // [P]
+  int *inpool;                    // node indices proven inside by the cull beyond the inline capacity
+  long long in_cap;
 };
 
 struct CacheArgs {
@@ -351,9 +358,10 @@ __global__ void cache_remap_kernel(PairArgs A, const int *old_half_off, const in
 
 // ---- A (fast path): cull from the candidate cache.  LPP lanes per pair (16: two pairs per warp; the typical pair has
 // ~40 candidates and ~15 survivors, so half warps keep the lanes busy and halve the dependent-load rounds per pair).
-__device__ __forceinline__ void store_pd(PdEntry *dst, long long off, int cnt, int ntrans, int nin, const unsigned short *in) {
+__device__ __forceinline__ void store_pd(PdEntry *dst, long long off, int cnt, int ntrans, int nin, const unsigned short *in,
+                                         unsigned int off2 = 0, int cnt2 = 0) {
   PdEntry e;
-  e.off = off; e.cnt = cnt; e.ntrans = ntrans; e.nin = (unsigned short)nin;
+  e.off = off; e.cnt = cnt; e.ntrans = (unsigned short)ntrans; e.nin = (unsigned short)nin; e.off2 = off2; e.cnt2 = (unsigned short)cnt2;
 #pragma unroll
   for (int q = 0; q < PD_INLINE; q++) e.in[q] = (in && q < nin) ? in[q] : (unsigned short)0;
   *dst = e;
@@ -490,13 +498,16 @@ __global__ void __launch_bounds__(WPB * 32, 32 / WPB) pair_cull_cached_kernel(Pa
     c2d0 += __popc(m2 & md0); c2d1 += __popc(m2 & ~md0);
   }
   // ---- one contiguous run per direction: [records to evaluate][inside nodes beyond the inline capacity]
-  const int r0 = c0d0 + max(0, c2d0 - PD_INLINE), r1 = c0d1 + max(0, c2d1 - PD_INLINE);
-  long long off0 = 0, off1 = 0;
+  // records to evaluate -> the target shape's pool; proven-inside nodes beyond the inline capacity -> the index pool
+  const int r0 = c0d0, r1 = c0d1, x0 = max(0, c2d0 - PD_INLINE), x1 = max(0, c2d1 - PD_INLINE);
+  long long off0 = 0, off1 = 0, xoff = 0;
   if (live && sl == 0 && r0 > 0) off0 = (long long)atomicAdd(&S.sc->pool_count[shp_j], (unsigned long long)r0);
   if (live && sl == 1 && r1 > 0) off1 = (long long)atomicAdd(&S.sc->pool_count[shp_i], (unsigned long long)r1);
+  if (live && sl == 2 && x0 + x1 > 0) xoff = (long long)atomicAdd(&S.sc->in_count, (unsigned long long)(x0 + x1));
   off0 = __shfl_sync(0xffffffffu, off0, shift);
   off1 = __shfl_sync(0xffffffffu, off1, shift + 1);
-  if (live && (off0 + r0 > S.pool_cap[shp_j] || off1 + r1 > S.pool_cap[shp_i])) big = true;   // pool full (the host grows it)
+  xoff = __shfl_sync(0xffffffffu, xoff, shift + 2);
+  if (live && (off0 + r0 > S.pool_cap[shp_j] || off1 + r1 > S.pool_cap[shp_i] || xoff + x0 + x1 > S.in_cap)) big = true;   // a pool is full (the host grows it)
   if (work && big && sl == 0) {   // deep contact or full pool: the fused kernel evaluates this pair (and counts it)
     store_pd(&S.pd[2 * p], 0, -1, 0, 0, nullptr);
     store_pd(&S.pd[2 * p + 1], 0, -1, 0, 0, nullptr);
@@ -523,7 +534,7 @@ __global__ void __launch_bounds__(WPB * 32, 32 / WPB) pair_cull_cached_kernel(Pa
       int slot = -1;
       if (fl == 0) slot = rank0;
       else if (rank2 < PD_INLINE) s_in[warp][sub][dirc][rank2] = (unsigned short)k;
-      else slot = (dirc ? c0d1 : c0d0) + (rank2 - PD_INLINE);
+      else S.inpool[xoff + (dirc ? x0 : 0) + (rank2 - PD_INLINE)] = k;
       if (slot >= 0) {
         const DevShape &sa = dirc ? sj : si;
         const double *M = s_dpose[warp][sub][dirc], *t = M + 9;
@@ -535,7 +546,7 @@ __global__ void __launch_bounds__(WPB * 32, 32 / WPB) pair_cull_cached_kernel(Pa
         r.k = k; r.flag = fl;
         const long long idx = (dirc ? base1 : base0) + slot;
         S.pool[idx] = r;
-        S.pool_flag[idx] = fl == 2 ? 1 : 0;
+        S.pool_flag[idx] = 0;
       }
     }
     w0d0 += __popc(m0 & md0); w0d1 += __popc(m0 & ~md0);
@@ -543,8 +554,8 @@ __global__ void __launch_bounds__(WPB * 32, 32 / WPB) pair_cull_cached_kernel(Pa
   }
   __syncwarp();
   if (wr && sl < 2) {
-    if (sl == 0) store_pd(&S.pd[2 * p], base0, r0, n0, min(c2d0, PD_INLINE), s_in[warp][sub][0]);
-    else store_pd(&S.pd[2 * p + 1], base1, r1, n1, min(c2d1, PD_INLINE), s_in[warp][sub][1]);
+    if (sl == 0) store_pd(&S.pd[2 * p], base0, r0, n0, min(c2d0, PD_INLINE), s_in[warp][sub][0], (unsigned int)xoff, x0);
+    else store_pd(&S.pd[2 * p + 1], base1, r1, n1, min(c2d1, PD_INLINE), s_in[warp][sub][1], (unsigned int)(xoff + x0), x1);
   }
 }
 
@@ -817,8 +828,9 @@ __global__ void __launch_bounds__(128, 6) pair_reduce_kernel(PairArgs A, SplitAr
     const int cnt0 = e0a.z, cnt1 = e1a.z;
     if (cnt0 >= 0) {   // else: deep contact, done (and counted) by the fused kernel
       const int i = A.pair_i[p], j = A.pair_j[p];
-      c_pairs = 1; c_trans = e0a.w + e1a.w; c_ghost = j >= A.nlocal;
-      const int nin0 = e0b.x & 0xffff, nin1 = e1b.x & 0xffff;
+      c_pairs = 1; c_trans = (e0a.w & 0xffff) + (e1a.w & 0xffff); c_ghost = j >= A.nlocal;
+      const int nin0 = e0b.y & 0xffff, nin1 = e1b.y & 0xffff;
+      const int xc0 = (e0a.w >> 16) & 0xffff, xc1 = (e1a.w >> 16) & 0xffff;     // proven-inside nodes in the index pool
       double out[14];
 #pragma unroll
       for (int r = 0; r < 14; r++) out[r] = 0.0;
@@ -826,7 +838,7 @@ __global__ void __launch_bounds__(128, 6) pair_reduce_kernel(PairArgs A, SplitAr
       const long long off0 = (long long)(((unsigned long long)(unsigned)e0a.y << 32) | (unsigned)e0a.x);
       const long long off1 = (long long)(((unsigned long long)(unsigned)e1a.y << 32) | (unsigned)e1a.x);
       unsigned long long msk0 = 0, msk1 = 0;
-      bool any = nin0 > 0 || nin1 > 0;
+      bool any = nin0 > 0 || nin1 > 0 || xc0 > 0 || xc1 > 0;
       {
         const int m0 = min(cnt0, 64), m1 = min(cnt1, 64);
         for (int r = 0; r < m0; r += 8) {
@@ -852,7 +864,7 @@ __global__ void __launch_bounds__(128, 6) pair_reduce_kernel(PairArgs A, SplitAr
           const DevShape &sa = A.shapes[dir ? shp_j : shp_i];
           const double sgn = dir ? -1.0 : 1.0;
           const long long off = dir ? off1 : off0;
-          const int cnt = dir ? cnt1 : cnt0, nin = dir ? nin1 : nin0;
+          const int cnt = dir ? cnt1 : cnt0, nin = dir ? nin1 : nin0, xc = dir ? xc1 : xc0;
           unsigned long long msk = dir ? msk1 : msk0;
           const int4 eb = dir ? e1b : e0b;
           NodeSums acc;
@@ -860,7 +872,7 @@ __global__ void __launch_bounds__(128, 6) pair_reduce_kernel(PairArgs A, SplitAr
           double Ra[9];
 #pragma unroll
           for (int e = 0; e < 9; e++) Ra[e] = A.Rs[e * st + a];
-          if (msk || nin > 0 || cnt > 64) {
+          if (msk || nin > 0 || cnt > 64 || xc > 0) {
             double x0[3];
 #pragma unroll
             for (int r = 0; r < 3; r++) {
@@ -878,9 +890,13 @@ __global__ void __launch_bounds__(128, 6) pair_reduce_kernel(PairArgs A, SplitAr
             }
             for (int r = 64; r < cnt; r++)
               if (S.pool_flag[off + r]) add_node(acc, nodes, nq, S.pool[off + r].k, x0);
-            // inline nodes (proven inside by the cull), in order
+            // nodes proven inside by the cull: the index-pool run, then the inline ones, in order
+            {
+              const unsigned xo = (unsigned)eb.x;
+              for (int r = 0; r < xc; r++) add_node(acc, nodes, nq, S.inpool[xo + r], x0);
+            }
             for (int q = 0; q < nin; q++) {
-              const int h = q + 1;                       // halfword index inside the second 16 B of the entry
+              const int h = q + 3;                       // halfword index inside the second 16 B of the entry (off2, nin, in[])
               const unsigned w = (h >> 1) == 0 ? (unsigned)eb.x : (h >> 1) == 1 ? (unsigned)eb.y : (h >> 1) == 2 ? (unsigned)eb.z : (unsigned)eb.w;
               add_node(acc, nodes, nq, (int)((w >> (16 * (h & 1))) & 0xffffu), x0);
             }

@@ -99,6 +99,8 @@ struct sh_ctx {
   DevBuf<SplitScalars> split_sc;
   DevBuf<EvalPlanDev> eval_plan;
   DevBuf<int> big_list, slow_list, split_flags;   // split_flags: [2]=cache overflow
+  DevBuf<int> inpool;                              // node indices proven inside by the cull beyond the inline capacity
+  long long h_in_cap = 0;
   std::vector<long long> h_pool_cap;
   unsigned long long *h_pool_count = nullptr;  // pinned scratch for cache builds
   SplitScalars *h_split_sc = nullptr;          // pinned: advisory read-back of the previous pair phase
@@ -472,6 +474,7 @@ int absorb_split_feedback(sh_ctx *h) {
       h->h_pool_cap[s] = (long long)(sc.pool_count[s] * 3 / 2) + 4096;
       h->pool_grows++;
     }
+  if ((long long)sc.in_count > h->h_in_cap * 9 / 10) { h->h_in_cap = (long long)(sc.in_count * 3 / 2) + 4096; h->pool_grows++; }
   h->last_records = 0;
   for (int s = 0; s < ns; s++) h->last_records += (long long)std::min<unsigned long long>(sc.pool_count[s], (unsigned long long)h->h_pool_cap[s]);
   // hard flag: that phase already ran on the window path; soft flag: rebuild now, while the cache is still valid
@@ -606,13 +609,15 @@ int run_split_pipeline(sh_ctx *h, PairArgs &P) {
   std::vector<long long> base(ns);
   long long tot = 0;
   for (int s2 = 0; s2 < ns; s2++) { base[s2] = tot; tot += h->h_pool_cap[s2]; }
-  try { h->pool.ensure((size_t)tot + 64); h->pool_flag.ensure((size_t)tot + 64); } catch (std::string &e) { return fail(h, e); }
+  if (h->h_in_cap < (long long)np * 2 + 4096) h->h_in_cap = (long long)np * 2 + 4096;
+  if (h->h_in_cap > 0xfffffff0LL) h->h_in_cap = 0xfffffff0LL;      // 32-bit offsets in the run descriptors
+  try { h->pool.ensure((size_t)tot + 64); h->pool_flag.ensure((size_t)tot + 64); h->inpool.ensure((size_t)h->h_in_cap + 64); } catch (std::string &e) { return fail(h, e); }
   CU(cudaMemcpyAsync(h->pool_base.p, base.data(), ns * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(h->pool_cap.p, h->h_pool_cap.data(), ns * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemsetAsync(h->split_sc.p, 0, sizeof(SplitScalars), h->stream));
   SplitArgs S;
   S.pool = h->pool.p; S.pool_flag = h->pool_flag.p; S.pool_base = h->pool_base.p; S.pool_cap = h->pool_cap.p; S.sc = h->split_sc.p;
-  S.pd = h->pd.p; S.big_list = h->big_list.p; S.slow_list = h->slow_list.p;
+  S.pd = h->pd.p; S.big_list = h->big_list.p; S.slow_list = h->slow_list.p; S.inpool = h->inpool.p; S.in_cap = h->h_in_cap;
   // ---- A
   if (tick(0)) return -2;
   if (C.enabled) {
@@ -849,7 +854,7 @@ int sh_destroy(sh_ctx *h) {
   for (auto &e : h->ev) cudaEventDestroy(e);
   for (auto &e : h->ev2) cudaEventDestroy(e);
   h->pool.release(); h->pool_flag.release(); h->pool_base.release(); h->pool_cap.release(); h->split_sc.release(); h->eval_plan.release(); h->slow_list.release();
-  h->pd.release(); h->big_list.release(); h->split_flags.release();
+  h->pd.release(); h->big_list.release(); h->split_flags.release(); h->inpool.release();
   for (int k = 0; k < 2; k++) { h->cache_hot[k].release(); h->cache_pool[k].release(); }
   h->old_c.release(); h->old_cc0.release(); h->old_cq0.release(); h->old_tag.release(); h->ghost_hash.release(); h->amap.release();
   h->old_half_off.release(); h->old_pair_j.release(); h->fresh_list.release(); h->cache_count.release(); h->cc0.release(); h->cq0.release(); h->drift.release();
@@ -1548,7 +1553,7 @@ int sh_get_timers(const sh_ctx *hc, double *seconds_pair, int64_t *pair_launches
   if (seconds_pair) *seconds_pair = h->sec_pair;
   if (pair_launches) *pair_launches = h->pair_launches;
   if (seconds_neigh) *seconds_neigh = h->sec_neigh;
-  if (seconds_other) *seconds_other = h->sec_other;
+  if (seconds_other) *seconds_other = h->sec_comm;   // ghost exchange, reverse communication, migration + borders
   return 0;
 }
 
