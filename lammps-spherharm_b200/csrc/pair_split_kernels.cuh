@@ -161,7 +161,8 @@ __device__ __forceinline__ int cube_cell(float f0, float f1, float f2, int cn) {
   if (ax >= ay && ax >= az) { face = f0 > 0 ? 0 : 1; ma = ax; uu = f1; vv = f2; }
   else if (ay >= az) { face = f1 > 0 ? 2 : 3; ma = ay; uu = f0; vv = f2; }
   else { face = f2 > 0 ? 4 : 5; ma = az; uu = f0; vv = f1; }
-  const float im = 1.0f / fmaxf(ma, 1e-30f), hn = 0.5f * (float)cn;
+  // (approximate reciprocal, 2 ulp: the tables' border strip of 1e-5 in (u, v) absorbs the index error)
+  const float im = __fdividef(1.0f, fmaxf(ma, 1e-30f)), hn = 0.5f * (float)cn;
   const int iu = min(cn - 1, max(0, (int)((uu * im + 1.0f) * hn)));
   const int iv = min(cn - 1, max(0, (int)((vv * im + 1.0f) * hn)));
   return (face * cn + iu) * cn + iv;
@@ -367,8 +368,18 @@ __device__ __forceinline__ void store_pd(PdEntry *dst, long long off, int cnt, i
   *dst = e;
 }
 
+// the per-shape fields the cached cull touches, handed over in the kernel's constant parameter space: a runtime-indexed
+// constant load instead of a chain of dependent global loads (pair -> shape id -> shape record -> table pointer -> table)
+struct ShapeLite {
+  const float4 *pf4; const float2 *cube_ul; const double *px, *py, *pz;
+  int cube_n, pad_;
+  double rmax, rmax2, rmin2;
+};
+struct ShapeLiteTable { ShapeLite s[SH_MAX_SHAPES]; };
+
 template <int WPB, int LPP>
-__global__ void __launch_bounds__(WPB * 32, 32 / WPB) pair_cull_cached_kernel(PairArgs A, SplitArgs S, CacheArgs C, int use_bounds) {
+__global__ void __launch_bounds__(WPB * 32, 32 / WPB) pair_cull_cached_kernel(PairArgs A, SplitArgs S, CacheArgs C, int use_bounds,
+                                                                              const __grid_constant__ ShapeLiteTable T) {
   constexpr int PPW = 32 / LPP, U = 2;
   constexpr unsigned FULLSUB = LPP == 32 ? 0xffffffffu : ((1u << LPP) - 1u);
   __shared__ double s_dpose[WPB][PPW][2][12];
@@ -398,7 +409,7 @@ __global__ void __launch_bounds__(WPB * 32, 32 / WPB) pair_cull_cached_kernel(Pa
   if (maxtot == 0) return;
   const bool work = ntot > 0;
   const int i = hot.i, j = hot.j, shp_i = hot.shp_i, shp_j = hot.shp_j;
-  const DevShape &si = A.shapes[shp_i], &sj = A.shapes[shp_j];
+  const ShapeLite &si = T.s[shp_i], &sj = T.s[shp_j];
   if (work) {   // relative poses of both directions (M, t): 24 elements spread over the pair's lanes
     const int st = A.stride;
     double d[3];
@@ -409,13 +420,20 @@ __global__ void __launch_bounds__(WPB * 32, 32 / WPB) pair_cull_cached_kernel(Pa
       if (n != 0) dk = dk - A.boxlen[k] * (double)n;
       d[k] = dk;
     }
-#pragma unroll
-    for (int e = sl; e < 24; e += LPP) {
-      const int half = e >= 12, l = e - 12 * half;
+    // M of direction 1 (= Rs_i^T Rs_j) is the transpose of M of direction 0 (= Rs_j^T Rs_i), bit for bit: the same three
+    // products in the same order, and a product does not depend on the order of its factors.  15 elements, one per lane:
+    // 0..8 M0 (and its transpose), 9..11 t0, 12..14 t1.
+    if (sl < 15) {
+      const int half = sl >= 12, l = half ? sl - 3 : sl;
       const double sgn = half ? -1.0 : 1.0;
       const double val = pose_element(A, half ? j : i, half ? i : j, sgn * d[0], sgn * d[1], sgn * d[2], l);
       s_dpose[warp][sub][half][l] = val;
       s_fpose[warp][sub][half][l] = (float)val;
+      if (sl < 9) {
+        const int r = sl / 3, k = sl - 3 * r;
+        s_dpose[warp][sub][1][3 * k + r] = val;
+        s_fpose[warp][sub][1][3 * k + r] = (float)val;
+      }
     }
   }
   __syncwarp();
@@ -483,8 +501,8 @@ __global__ void __launch_bounds__(WPB * 32, 32 / WPB) pair_cull_cached_kernel(Pa
     int fl = -1;
     if (live && g < nsurv) {
       const int dirc = g >= ns0, k = surv[g];
-      const DevShape &sa = dirc ? sj : si;
-      const DevShape &sb = dirc ? si : sj;
+      const ShapeLite &sa = dirc ? sj : si;
+      const ShapeLite &sb = dirc ? si : sj;
       const double *M = s_dpose[warp][sub][dirc];
       double s0, s1, s2;
       fl = exact_node_stage(M, M + 9, sa.px[k], sa.py[k], sa.pz[k], sb.rmax2, sb.rmin2, sb.cube_ul, sb.cube_n, use_bounds, s0, s1, s2);
@@ -536,7 +554,7 @@ __global__ void __launch_bounds__(WPB * 32, 32 / WPB) pair_cull_cached_kernel(Pa
       else if (rank2 < PD_INLINE) s_in[warp][sub][dirc][rank2] = (unsigned short)k;
       else S.inpool[xoff + (dirc ? x0 : 0) + (rank2 - PD_INLINE)] = k;
       if (slot >= 0) {
-        const DevShape &sa = dirc ? sj : si;
+        const ShapeLite &sa = dirc ? sj : si;
         const double *M = s_dpose[warp][sub][dirc], *t = M + 9;
         const double p0 = sa.px[k], p1 = sa.py[k], p2 = sa.pz[k];
         SurvRec r;

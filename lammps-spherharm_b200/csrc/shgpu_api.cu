@@ -625,7 +625,13 @@ int run_split_pipeline(sh_ctx *h, PairArgs &P) {
     const int cw = h->tune_cull_wpb > 0 ? h->tune_cull_wpb : 1;
     const int ppw = h->tune_cull_lpp == 32 ? 1 : 2;
     const int grid = cdiv(np, cw * ppw);
-#define LAUNCH_CULL(W, L) pair_cull_cached_kernel<W, L><<<grid, W * 32, 0, h->stream>>>(P, S, C, use_bounds)
+    ShapeLiteTable T{};
+    for (int s2 = 0; s2 < ns && s2 < SH_MAX_SHAPES; s2++) {
+      const DevShape &v = h->shape_host_view[s2];
+      T.s[s2].pf4 = v.pf4; T.s[s2].cube_ul = v.cube_ul; T.s[s2].px = v.px; T.s[s2].py = v.py; T.s[s2].pz = v.pz;
+      T.s[s2].cube_n = v.cube_n; T.s[s2].rmax = v.rmax; T.s[s2].rmax2 = v.rmax2; T.s[s2].rmin2 = v.rmin2;
+    }
+#define LAUNCH_CULL(W, L) pair_cull_cached_kernel<W, L><<<grid, W * 32, 0, h->stream>>>(P, S, C, use_bounds, T)
     if (ppw == 1) { if (cw == 1) LAUNCH_CULL(1, 32); else if (cw == 2) LAUNCH_CULL(2, 32); else if (cw == 8) LAUNCH_CULL(8, 32); else LAUNCH_CULL(4, 32); }
     else { if (cw == 1) LAUNCH_CULL(1, 16); else if (cw == 2) LAUNCH_CULL(2, 16); else if (cw == 8) LAUNCH_CULL(8, 16); else LAUNCH_CULL(4, 16); }
 #undef LAUNCH_CULL
