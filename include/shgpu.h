@@ -8,8 +8,8 @@
  * quaternion integrator, wall fixes"); see SURVEY.md §8(b) and INTEGRATION.md for the binding a
  * LAMMPS maintainer would add on the reference side.
  *
- * Conventions: every call returns int (0 = OK, <0 = error; text via sh_last_error).  No C++
- * exception crosses the boundary.  The handle is opaque, owned by the library and not thread-safe
+ * Conventions: every call returns int (0 = OK, <0 = error; text via sh_last_error; -99 = an internal
+ * C++ exception such as std::bad_alloc was caught at the boundary).  No C++ exception crosses the boundary.  The handle is opaque, owned by the library and not thread-safe
  * (one host thread drives one handle, bound to one CUDA device).  Host arrays passed in are copied;
  * arrays passed out are filled into caller-owned buffers of the stated length (NULL = skip).
  * Reals are double, indices int32, tags int64.  Per-atom vectors are AoS rows (n x 3, quaternion

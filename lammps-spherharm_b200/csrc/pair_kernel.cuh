@@ -64,7 +64,7 @@ __device__ __forceinline__ void pair_separation(const PairArgs &A, int p, int i,
   }
 }
 
-// oracle A.5b (sh_oracle.c contact_dissipation), same operations in the same order.  out: [2..4] F on i, [5..7] tau_i,
+// the CPU checker's contact_dissipation (spec A.5b), same operations in the same order.  out: [2..4] F on i, [5..7] tau_i,
 // [8..10] tau_j, [11..13] overlap centroid (i's periodic image); d = c_i - c_j (minimum image); lj = c_j - x_j.
 __device__ __forceinline__ void contact_dissipation(const PairArgs &A, int i, int j, int shp_i, int shp_j, const double d[3],
                                                     const double lj[3], double out[14]) {

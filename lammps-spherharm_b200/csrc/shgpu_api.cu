@@ -906,7 +906,7 @@ int sh_set_quadrature(sh_ctx *h, int n_theta, int n_phi) {
   return 0;
 }
 
-int sh_add_shape(sh_ctx *h, int lmax, const double *a_lm, const double *b_lm, double density, int *shape_id_out) {
+int sh_add_shape(sh_ctx *h, int lmax, const double *a_lm, const double *b_lm, double density, int *shape_id_out) try {
   if ((int)h->shapes.size() >= SH_MAX_SHAPES) return fail(h, "too many shapes");
   ShapeTables t;
   std::string e = build_shape_tables(lmax, a_lm, b_lm, density, h->n_theta, h->n_phi, t, h->cube_n);
@@ -915,7 +915,7 @@ int sh_add_shape(sh_ctx *h, int lmax, const double *a_lm, const double *b_lm, do
   h->shapes_dirty = true; h->forces_valid = false; h->list_valid = false;
   if (shape_id_out) *shape_id_out = (int)h->shapes.size() - 1;
   return 0;
-}
+} catch (...) { return -99; }   // no C++ exception crosses the C ABI (out of memory / internal error)
 
 int sh_get_shape_props(const sh_ctx *h, int shape, double *volume, double com[3], double inertia[3],
                        double quat_principal[4], double *rmax, double *rmin) {
@@ -939,7 +939,7 @@ int sh_get_nodes(const sh_ctx *h, int shape, double *p, double *nds) {
 }
 
 int sh_set_atoms(sh_ctx *h, int64_t n_in, const int64_t *tag_in, const int *shape_in, const double *x_in, const double *v_in,
-                 const double *quat_in, const double *angmom_in) {
+                 const double *quat_in, const double *angmom_in) try {
   if (n_in < 0 || n_in > (int64_t)1 << 30) return fail(h, "bad atom count");
   if (n_in > 0 && (!shape_in || !x_in)) return fail(h, "shape and x are required");
   const int ns = (int)h->shapes.size();
@@ -1012,7 +1012,7 @@ int sh_set_atoms(sh_ctx *h, int64_t n_in, const int64_t *tag_in, const int *shap
   h->atoms_epoch++; h->cache_state = CACHE_INVALID;
   h->dd.borders_ok = false;
   return 0;
-}
+} catch (...) { return -99; }   // no C++ exception crosses the C ABI (out of memory / internal error)
 
 int sh_pair_coeff(sh_ctx *h, int si, int sj, double k, double exponent) {
   if (si < 0 || sj < 0 || si >= SH_MAX_SHAPES || sj >= SH_MAX_SHAPES) return fail(h, "pair_coeff: shape out of range");
@@ -1075,14 +1075,14 @@ int sh_set_pair_tuning(sh_ctx *h, int threads_per_cta, int ctas_per_sm, int vari
   return 0;
 }
 
-int sh_compute_forces(sh_ctx *h) {
+int sh_compute_forces(sh_ctx *h) try {
   CU(cudaSetDevice(h->device));
   int rc = setup_forces(h);
   if (rc) return rc;
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaGetLastError());
   return 0;
-}
+} catch (...) { return -99; }   // no C++ exception crosses the C ABI (out of memory / internal error)
 
 // ---- one timestep in two halves, so that a multi-rank driver can put the ghost exchange between them
 namespace {
@@ -1200,7 +1200,7 @@ int step_once(sh_ctx *h) {
 }
 }  // namespace
 
-int sh_step_begin(sh_ctx *h, int *rebuild_wanted) {
+int sh_step_begin(sh_ctx *h, int *rebuild_wanted) try {
   CU(cudaSetDevice(h->device));
   int rc;
   if (!h->forces_valid || !h->list_valid) { if ((rc = setup_forces(h))) return rc; }
@@ -1219,15 +1219,15 @@ int sh_step_begin(sh_ctx *h, int *rebuild_wanted) {
   }
   if (rebuild_wanted) *rebuild_wanted = rebuild ? 1 : 0;
   return 0;
-}
+} catch (...) { return -99; }   // no C++ exception crosses the C ABI (out of memory / internal error)
 
-int sh_step_end(sh_ctx *h, int rebuild) {
+int sh_step_end(sh_ctx *h, int rebuild) try {
   CU(cudaSetDevice(h->device));
   if (h->n == 0) return 0;
   return step_finish(h, rebuild);
-}
+} catch (...) { return -99; }   // no C++ exception crosses the C ABI (out of memory / internal error)
 
-int sh_run(sh_ctx *h, int64_t nsteps) {
+int sh_run(sh_ctx *h, int64_t nsteps) try {
   CU(cudaSetDevice(h->device));
   int rc;
   if (!h->forces_valid || !h->list_valid) { if ((rc = setup_forces(h))) return rc; }
@@ -1265,7 +1265,7 @@ int sh_run(sh_ctx *h, int64_t nsteps) {
                    "rebuild on (increase the skin, or sh_set_tuning \"sync_rebuild\" 1)");
   }
   return 0;
-}
+} catch (...) { return -99; }   // no C++ exception crosses the C ABI (out of memory / internal error)
 
 // ---- multi-rank support: the last nghost atoms of the arrays are ghosts (copies of atoms owned by
 // other ranks / periodic images): they take part in pairs with owned atoms but receive no force,
@@ -1326,7 +1326,7 @@ int sh_get_run_time(const sh_ctx *h, double *seconds_last_run, double *seconds_t
 
 // Pair::compute-style offload: the caller owns the atoms, pushes x / quat (and optionally v, angmom)
 // every step, keeps the neighbor list alive across calls (rebuilt when the skin is exhausted).
-int sh_put_state(sh_ctx *h, int64_t n, const double *x, const double *v, const double *quat, const double *angmom) {
+int sh_put_state(sh_ctx *h, int64_t n, const double *x, const double *v, const double *quat, const double *angmom) try {
   if (n != h->n) return fail(h, "put_state: n mismatch");
   CU(cudaSetDevice(h->device));
   if (n == 0) return 0;
@@ -1343,9 +1343,9 @@ int sh_put_state(sh_ctx *h, int64_t n, const double *x, const double *v, const d
   CU(cudaStreamSynchronize(h->stream));
   h->forces_valid = false;
   return 0;
-}
+} catch (...) { return -99; }   // no C++ exception crosses the C ABI (out of memory / internal error)
 
-int sh_get_forces(const sh_ctx *hc, int64_t n, double *f, double *torque) {
+int sh_get_forces(const sh_ctx *hc, int64_t n, double *f, double *torque) try {
   sh_ctx *h = const_cast<sh_ctx *>(hc);
   if (n < 0 || n > h->n) return fail(h, "get_forces: n out of range");
   CU(cudaSetDevice(h->device));
@@ -1359,14 +1359,14 @@ int sh_get_forces(const sh_ctx *hc, int64_t n, double *f, double *torque) {
   if (torque) CU(cudaMemcpyAsync(torque, h->stage.p + 3 * n, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return 0;
-}
+} catch (...) { return -99; }   // no C++ exception crosses the C ABI (out of memory / internal error)
 
 // ---- checkpoint / resume (write_restart / read_restart of the atom style: AtomVec::pack_restart): binary
 // snapshot of the owned atoms.  Shapes, coefficients and fixes are re-issued by the input script, as in LAMMPS.
 namespace {
 struct SnapHeader { char magic[8]; int32_t version, nshapes; int64_t n, step; double lo[3], hi[3]; int32_t periodic[3], pad; };
 }
-int sh_write_snapshot(const sh_ctx *hc, const char *path, int64_t step) {
+int sh_write_snapshot(const sh_ctx *hc, const char *path, int64_t step) try {
   sh_ctx *h = const_cast<sh_ctx *>(hc);
   const int64_t n = h->n - h->nghost;
   { int rc = sync_tags_host(h); if (rc) return rc; }
@@ -1387,8 +1387,8 @@ int sh_write_snapshot(const sh_ctx *hc, const char *path, int64_t step) {
   fclose(f);
   if (!ok) return fail(h, "short write to snapshot file");
   return 0;
-}
-int sh_read_snapshot(sh_ctx *h, const char *path, int64_t *step_out) {
+} catch (...) { return -99; }   // no C++ exception crosses the C ABI (out of memory / internal error)
+int sh_read_snapshot(sh_ctx *h, const char *path, int64_t *step_out) try {
   FILE *f = fopen(path, "rb");
   if (!f) return fail(h, std::string("cannot open snapshot file ") + path);
   SnapHeader hd{};
@@ -1396,6 +1396,13 @@ int sh_read_snapshot(sh_ctx *h, const char *path, int64_t *step_out) {
   if (hd.nshapes != (int)h->shapes.size()) { fclose(f); return fail(h, "snapshot was written with a different number of shapes"); }
   const int64_t n = hd.n;
   if (n < 0 || n > ((int64_t)1 << 30)) { fclose(f); return fail(h, "bad atom count in snapshot"); }
+  {   // the payload must really be there before anything is allocated for it
+    const long pos = ftell(f);
+    fseek(f, 0, SEEK_END);
+    const long end = ftell(f);
+    fseek(f, pos, SEEK_SET);
+    if (end - pos < (long)(n * (int64_t)(sizeof(int64_t) + sizeof(int) + 13 * sizeof(double)))) { fclose(f); return fail(h, "truncated snapshot file"); }
+  }
   std::vector<int64_t> tag(n); std::vector<int> shp(n);
   std::vector<double> x(3 * n), v(3 * n), q(4 * n), L(3 * n);
   bool ok = n == 0 || (fread(tag.data(), sizeof(int64_t), n, f) == (size_t)n && fread(shp.data(), sizeof(int), n, f) == (size_t)n &&
@@ -1409,11 +1416,11 @@ int sh_read_snapshot(sh_ctx *h, const char *path, int64_t *step_out) {
   if (rc) return rc;
   if (step_out) *step_out = hd.step;
   return 0;
-}
+} catch (...) { return -99; }   // no C++ exception crosses the C ABI (out of memory / internal error)
 
 int sh_get_natoms(const sh_ctx *h, int64_t *n) { if (n) *n = h->n; return 0; }
 
-int sh_get_atoms(const sh_ctx *hc, int64_t n, double *x, double *v, double *quat, double *angmom, double *f, double *torque) {
+int sh_get_atoms(const sh_ctx *hc, int64_t n, double *x, double *v, double *quat, double *angmom, double *f, double *torque) try {
   sh_ctx *h = const_cast<sh_ctx *>(hc);
   if (n < 0 || n > h->n) return fail(h, "get_atoms: n out of range");
   CU(cudaSetDevice(h->device));
@@ -1430,10 +1437,10 @@ int sh_get_atoms(const sh_ctx *hc, int64_t n, double *x, double *v, double *quat
   CU(down(h->x, x, 3)); CU(down(h->v, v, 3)); CU(down(h->q, quat, 4)); CU(down(h->L, angmom, 3));
   CU(down(h->f, f, 3)); CU(down(h->tq, torque, 3));
   return 0;
-}
+} catch (...) { return -99; }   // no C++ exception crosses the C ABI (out of memory / internal error)
 
 int sh_get_pairs(const sh_ctx *hc, int64_t cap, int64_t *npairs, int64_t *tag_i, int64_t *tag_j, double *V, double *F,
-                 double *tau_i, double *tau_j, double *centroid) {
+                 double *tau_i, double *tau_j, double *centroid) try {
   sh_ctx *h = const_cast<sh_ctx *>(hc);
   CU(cudaSetDevice(h->device));
   CU(cudaStreamSynchronize(h->stream));
@@ -1460,9 +1467,9 @@ int sh_get_pairs(const sh_ctx *hc, int64_t cap, int64_t *npairs, int64_t *tag_i,
     }
   }
   return 0;
-}
+} catch (...) { return -99; }   // no C++ exception crosses the C ABI (out of memory / internal error)
 
-int sh_get_energy(const sh_ctx *hc, double *ke_trans, double *ke_rot, double *e_contact) {
+int sh_get_energy(const sh_ctx *hc, double *ke_trans, double *ke_rot, double *e_contact) try {
   sh_ctx *h = const_cast<sh_ctx *>(hc);
   CU(cudaSetDevice(h->device));
   const int n = (int)(h->n - h->nghost);
@@ -1493,10 +1500,10 @@ int sh_get_energy(const sh_ctx *hc, double *ke_trans, double *ke_rot, double *e_
   if (ke_rot) *ke_rot = kr;
   if (e_contact) *e_contact = ec;
   return 0;
-}
+} catch (...) { return -99; }   // no C++ exception crosses the C ABI (out of memory / internal error)
 
 // pressure-tensor sums of this rank (compute pressure in LAMMPS terms): fixed-order two-level reduction, no FP atomics
-int sh_get_stress(const sh_ctx *hc, double virial[9], double kinetic[9]) {
+int sh_get_stress(const sh_ctx *hc, double virial[9], double kinetic[9]) try {
   sh_ctx *h = const_cast<sh_ctx *>(hc);
   CU(cudaSetDevice(h->device));
   const int n = (int)(h->n - h->nghost), np = h->forces_valid ? h->npairs : 0;
@@ -1522,7 +1529,7 @@ int sh_get_stress(const sh_ctx *hc, double virial[9], double kinetic[9]) {
   if (np > 0) for (int b = 0; b < nb_pairs; b++) for (int k = 0; k < 9; k++) W[k] += part[(size_t)9 * (nb_atoms + b) + k];
   for (int k = 0; k < 9; k++) { if (virial) virial[k] = W[k]; if (kinetic) kinetic[k] = K[k]; }
   return 0;
-}
+} catch (...) { return -99; }   // no C++ exception crosses the C ABI (out of memory / internal error)
 
 int sh_get_ghost_pair_evals(const sh_ctx *hc, int64_t *ghost_pair_evals) {
   sh_ctx *h = const_cast<sh_ctx *>(hc);
@@ -1627,7 +1634,7 @@ int sh_get_cache_stats(const sh_ctx *hc, int64_t *cache_builds, double *seconds_
   return 0;
 }
 
-int sh_set_tuning(sh_ctx *h, const char *key, double value) {
+int sh_set_tuning(sh_ctx *h, const char *key, double value) try {
   if (!h || !key) return -1;
   const std::string k(key);
   const int v = (int)value;
@@ -1647,7 +1654,7 @@ int sh_set_tuning(sh_ctx *h, const char *key, double value) {
   else if (k == "sync_rebuild") { h->lag_mode = v == 0; h->lag_pending = false; }
   else return fail(h, "unknown tuning key: " + k);
   return 0;
-}
+} catch (...) { return -99; }   // no C++ exception crosses the C ABI (out of memory / internal error)
 
 int sh_measure_fp64_peak(sh_ctx *h, double *flops_per_s, double *sm_clock_mhz_est) {
   CU(cudaSetDevice(h->device));
@@ -1687,7 +1694,7 @@ int sh_dd_unique_id(char *id, int cap) {
   return 0;
 }
 
-int sh_dd_init(sh_ctx *h, int rank, int nranks, const char *id, const int *pgrid) {
+int sh_dd_init(sh_ctx *h, int rank, int nranks, const char *id, const int *pgrid) try {
   if (!h) return -1;
   if (nranks < 1 || nranks > DD_MAX_RANKS || rank < 0 || rank >= nranks) return fail(h, "dd_init: bad rank / nranks (at most 64 ranks)");
   if (h->dd.on) return fail(h, "dd_init: already initialised");
@@ -1707,7 +1714,7 @@ int sh_dd_init(sh_ctx *h, int rank, int nranks, const char *id, const int *pgrid
   h->forces_valid = false; h->list_valid = false;
   if (h->n > 0) return fail(h, "dd_init must precede sh_set_atoms");
   return 0;
-}
+} catch (...) { return -99; }   // no C++ exception crosses the C ABI (out of memory / internal error)
 
 int sh_dd_get_info(const sh_ctx *hc, int pgrid[3], int brick[3], int64_t *nlocal, int64_t *nghost, int64_t *migrated,
                    int64_t *border_builds) {
@@ -1730,7 +1737,7 @@ int sh_get_step_trace(const sh_ctx *h, int64_t cap, int64_t *nsteps, double *ms,
   return 0;
 }
 
-int sh_get_tags(const sh_ctx *hc, int64_t n, int64_t *tags) {
+int sh_get_tags(const sh_ctx *hc, int64_t n, int64_t *tags) try {
   sh_ctx *h = const_cast<sh_ctx *>(hc);
   if (n < 0 || n > h->n) return fail(h, "get_tags: n out of range");
   CU(cudaSetDevice(h->device));
@@ -1738,7 +1745,7 @@ int sh_get_tags(const sh_ctx *hc, int64_t n, int64_t *tags) {
   if (rc) return rc;
   for (int64_t i = 0; i < n; i++) tags[i] = h->tag[i];
   return 0;
-}
+} catch (...) { return -99; }   // no C++ exception crosses the C ABI (out of memory / internal error)
 
 // Lees-Edwards shear (fix deform xy ... remap v): flow along x, gradient along y, rate = d(v_x)/dy.  Images across the
 // periodic y boundary are ghosts displaced by rate * Ly * t along x; uses the decomposition machinery even on one GPU.

@@ -23,7 +23,8 @@ def shlmp(script_text=None, script_file=None, cwd=EX):
 
 
 @pytest.mark.parametrize("script,expect", [("in.two_particle", "run 1200 with 2 atoms, 1 shape(s), 0 wall(s) OK"),
-                                           ("in.wall_settle", "run 5000 with 1000 atoms, 1 shape(s), 1 wall(s) OK")])
+                                           ("in.wall_settle", "run 5000 with 1000 atoms, 1 shape(s), 1 wall(s) OK"),
+                                           ("in.shear_box", "run 300 with 320 atoms, 1 shape(s), 0 wall(s) OK")])
 def test_examples_parse(script, expect):
     res = shlmp(script_file=script)
     assert res.returncode == 0, res.stderr
@@ -46,8 +47,20 @@ HEAD = "atom_style spherharm 20 32 64 ellipsoid_l20.sh\nregion box block -5 5 -5
     (HEAD + "pair_style spherharm\nfoo bar\n", "Unknown command: foo"),
     ("atom_style spherharm 20 32 64 ellipsoid_l20.sh\npair_style spherharm\nrun 1\n", "Box must be defined before run"),
     (HEAD + "timestep -1\n", "Illegal timestep command"),
+    (HEAD + "pair_style spherharm\npair_coeff 1 1 1000 1 0.5\n", "Incorrect args for pair coefficients"),
+    (HEAD + "pair_style spherharm\npair_coeff 1 1 1000 1 -1 0 0\n", "Incorrect args for pair coefficients"),
+    (HEAD + "fix 2 all deform 1 xz erate 0.1 remap v\n", "Only fix deform N xy erate <rate> remap v is supported"),
+    (HEAD + "boundary p f p\npair_style spherharm\nfix 2 all deform 1 xy erate 0.1 remap v\nrun 1\n", "fix deform xy needs a box periodic in x and y"),
 ])
 def test_malformed_scripts_are_rejected(text, msg):
     res = shlmp(script_text=text)
     assert res.returncode == 1
     assert "ERROR: " + msg in res.stderr, res.stderr
+
+
+def test_dissipative_pair_coeff_and_gpus_flag_are_accepted():
+    res = shlmp(script_text=HEAD + "pair_style spherharm\npair_coeff 1 1 1000 1 3.0 2.0 0.4\ncreate_atoms 1 single 0 0 0\nrun 5\n")
+    assert res.returncode == 0 and "run 5 with 1 atoms" in res.stdout, res.stderr
+    from lammps_spherharm_b200 import build as b
+    r2 = subprocess.run([b.build_host(), "-check", "-gpus", "4", "-in", "in.shear_box"], cwd=EX, capture_output=True, text=True, timeout=120)
+    assert r2.returncode == 0 and "OK" in r2.stdout, r2.stderr
