@@ -167,6 +167,9 @@ int sh_set_pair_tuning(sh_ctx *h, int threads_per_cta, int ctas_per_sm, int vari
  * "cube_n" direction cells per cube-face edge of the per-shape bound tables (8..144, default 144; before sh_add_shape);
  * "sync_rebuild" 1 = sh_run decides neighbor rebuilds from the current step's displacement flag (one host round trip per
  * step) instead of the one-step-ahead prediction (default 0: the host never waits for the device inside sh_run);
+ * "peer_exchange" (in-library decomposition, more than one rank; default 1) 1 = the per-step ghost exchange and force
+ * return go through NVLink peer memory: the pack kernels store straight into the neighbours' inboxes (CUDA IPC between
+ * processes, peer access between rank threads) and a one-warp kernel exchanges sequence flags; 0 = NCCL send/recv;
  * "newton" (in-library decomposition; default 1) 1 = a pair that straddles a rank boundary is evaluated by one rank (chosen
  * from the two tags) and the force / torque on the ghost is returned to its owner every step (reverse communication, 48 B
  * per ghost); 0 = both ranks evaluate it and keep their own half (no return trip);

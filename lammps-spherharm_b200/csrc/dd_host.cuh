@@ -6,6 +6,7 @@
 // packing) is done by the kernels in decomp_kernels.cuh; the host reads back ~30 counters per neighbor rebuild.
 #pragma once
 #include <dlfcn.h>
+#include <unistd.h>
 
 namespace {
 
@@ -19,7 +20,7 @@ NcclApi *nccl_api() {
   if (!api.lib) { api.err = "NCCL not found (dlopen libnccl.so.2)"; return nullptr; }
 #define SHGPU_NCCL_SYM(field, name) *(void **)(&api.field) = dlsym(api.lib, name); if (!api.field) { api.err = std::string("NCCL symbol missing: ") + name; api.lib = nullptr; return nullptr; }
   SHGPU_NCCL_SYM(GetUniqueId, "ncclGetUniqueId") SHGPU_NCCL_SYM(CommInitRank, "ncclCommInitRank") SHGPU_NCCL_SYM(CommDestroy, "ncclCommDestroy")
-  SHGPU_NCCL_SYM(Send, "ncclSend") SHGPU_NCCL_SYM(Recv, "ncclRecv") SHGPU_NCCL_SYM(AllReduce, "ncclAllReduce")
+  SHGPU_NCCL_SYM(Send, "ncclSend") SHGPU_NCCL_SYM(Recv, "ncclRecv") SHGPU_NCCL_SYM(AllReduce, "ncclAllReduce") SHGPU_NCCL_SYM(AllGather, "ncclAllGather")
   SHGPU_NCCL_SYM(GroupStart, "ncclGroupStart") SHGPU_NCCL_SYM(GroupEnd, "ncclGroupEnd") SHGPU_NCCL_SYM(GetErrorString, "ncclGetErrorString")
 #undef SHGPU_NCCL_SYM
   return &api;
@@ -204,6 +205,89 @@ int dd_exchange_counts(sh_ctx *h, const std::vector<int> &ranks, const int *d_s,
   return 0;
 }
 
+// ---- NVLink peer-memory inboxes (PeerCtx in dd_types.h) --------------------------------------------------------------
+struct PeerBlob { cudaIpcMemHandle_t handle; long long pid, ptr, capF, capR; int device, ok; char pad[128 - 64 - 4 * 8 - 2 * 4]; };
+static_assert(sizeof(PeerBlob) == 128, "PeerBlob is exchanged as 128 bytes");
+
+void dd_peer_release(sh_ctx *h) {
+  PeerCtx &P = h->dd.peer;
+  for (void *q : P.opened) cudaIpcCloseMemHandle(q);
+  P.opened.clear(); P.base.clear();
+  if (P.region) { cudaFree(P.region); P.region = nullptr; }
+  P.enabled = false;
+}
+
+// COLLECTIVE over all ranks: (re)allocate this rank's inbox region for at least needF / needR records, exchange the IPC handles
+// and open the neighbours' regions.  Any rank failing switches the peer path off everywhere (NCCL keeps working).
+int dd_peer_setup(sh_ctx *h, long long needF, long long needR) {
+  DdCtx &D = h->dd;
+  PeerCtx &P = D.peer;
+  CU(cudaStreamSynchronize(h->stream));
+  dd_peer_release(h);
+  P.capF = std::max<long long>(4096, 2 * needF); P.capR = std::max<long long>(4096, 2 * needR);
+  const size_t nd = (size_t)2 * P.capF * P.wmax + (size_t)2 * P.capR * 6 + 2 * DD_MAX_RANKS;
+  PeerBlob mine{};
+  mine.ok = 1;
+  if (cudaMalloc(&P.region, nd * sizeof(double)) != cudaSuccess) { P.region = nullptr; mine.ok = 0; cudaGetLastError(); }
+  if (mine.ok) {
+    cudaMemset(P.region, 0, nd * sizeof(double));
+    if (cudaIpcGetMemHandle(&mine.handle, P.region) != cudaSuccess) { mine.ok = 0; cudaGetLastError(); }
+  }
+  if (!P.d_err) { CU(cudaMalloc(&P.d_err, sizeof(int))); CU(cudaMemset(P.d_err, 0, sizeof(int))); }
+  mine.pid = (long long)getpid(); mine.ptr = (long long)(uintptr_t)P.region; mine.capF = P.capF; mine.capR = P.capR; mine.device = h->device;
+  DevBuf<char> d_blobs;
+  try { d_blobs.ensure((size_t)128 * (D.nranks + 1)); P.d_off.ensure(64); } catch (std::string &e) { return fail(h, e); }
+  CU(cudaMemcpy(d_blobs.p + (size_t)128 * D.nranks, &mine, 128, cudaMemcpyHostToDevice));
+  NC(D.nccl->AllGather(d_blobs.p + (size_t)128 * D.nranks, d_blobs.p, 128, ncclChar, D.comm, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  std::vector<PeerBlob> all(D.nranks);
+  CU(cudaMemcpy(all.data(), d_blobs.p, (size_t)128 * D.nranks, cudaMemcpyDeviceToHost));
+  d_blobs.release();
+  bool ok = true;
+  for (auto &b : all) ok = ok && b.ok;
+  const int nnb = (int)D.nbr_rank.size();
+  P.base.assign(nnb, nullptr); P.pcapF.assign(nnb, 0); P.pcapR.assign(nnb, 0);
+  for (int k = 0; k < nnb && ok; k++) {
+    const int r = D.nbr_rank[k];
+    const PeerBlob &b = all[r];
+    P.pcapF[k] = b.capF; P.pcapR[k] = b.capR;
+    if (r == D.rank) { P.base[k] = P.region; continue; }
+    if (b.pid == mine.pid) {            // rank threads of one process: plain peer access
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, h->device, b.device);
+      if (!can) { ok = false; break; }
+      cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = false;
+      cudaGetLastError();
+      P.base[k] = (double *)(uintptr_t)b.ptr;
+    } else {
+      void *q = nullptr;
+      if (cudaIpcOpenMemHandle(&q, b.handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; cudaGetLastError(); break; }
+      P.opened.push_back(q);
+      P.base[k] = (double *)q;
+    }
+  }
+  // everybody or nobody
+  int *d_ok = h->dd.d_int.p + 250;
+  const int myok = ok ? 1 : 0;
+  CU(cudaMemcpy(d_ok, &myok, sizeof(int), cudaMemcpyHostToDevice));
+  NC(D.nccl->AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, D.comm, h->stream));
+  int allok = 0;
+  CU(cudaMemcpyAsync(&allok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (!allok) { dd_peer_release(h); P.want = false; return 0; }
+  P.enabled = true; P.seq_f = 0; P.seq_r = 0;
+  return 0;
+}
+
+double *peer_inbox(const PeerCtx &P, double *base, long long capF, long long capR, bool reverse, int parity, int wmax) {
+  (void)P;
+  return reverse ? base + (size_t)2 * capF * wmax + (size_t)parity * capR * 6 : base + (size_t)parity * capF * wmax;
+}
+unsigned long long *peer_flags(double *base, long long capF, long long capR, bool reverse, int wmax) {
+  return reinterpret_cast<unsigned long long *>(base + (size_t)2 * capF * wmax + (size_t)2 * capR * 6) + (reverse ? DD_MAX_RANKS : 0);
+}
+
 int dd_width(const sh_ctx *h, bool full) { return (full ? 2 : 0) + 7 + (h->dd.ghost_vel ? 6 : 0); }
 
 // Comm::exchange: wrap, find owners, move the atoms that left this brick to their new owners (device compaction)
@@ -312,6 +396,43 @@ int dd_borders(sh_ctx *h) {
   int nsend = 0, nghost = 0;
   for (int k = 0; k < nnb; k++) { D.send_cnt[k] = D.h_int[64 + k]; D.recv_cnt[k] = D.h_int[96 + k]; nsend += D.send_cnt[k]; nghost += D.recv_cnt[k]; }
   D.nsend = nsend;
+  // ---- NVLink peer path: inbox capacities (global decision) and this rank's offsets inside its neighbours' inboxes
+  if (D.nranks > 1 && D.peer.want) {
+    PeerCtx &P = D.peer;
+    int *d_need = D.d_int.p + 240;
+    const int need[2] = {P.enabled ? (nghost > P.capF || nsend > P.capR ? 1 : 0) : 1, 0};
+    CU(cudaMemcpyAsync(d_need, need, 2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    NC(D.nccl->AllReduce(d_need, d_need, 1, ncclInt, ncclMax, D.comm, h->stream));
+    CU(cudaMemcpyAsync(D.h_int + 240, d_need, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (D.h_int[240]) { if ((rc2 = dd_peer_setup(h, nghost, nsend))) return rc2; }
+    if (P.enabled) {
+      // neighbour k writes its ghosts for me at record roff[k] of my F inbox, and returns forces at soff[k] of my R inbox
+      long long offs[64] = {0};
+      long long ro = 0, so = 0;
+      for (int k = 0; k < nnb; k++) { offs[k] = ro; offs[32 + k] = so; ro += D.recv_cnt[k]; so += D.send_cnt[k]; }
+      try { D.recvbuf.ensure(256); } catch (std::string &e) { return fail(h, e); }
+      long long *d_mine = reinterpret_cast<long long *>(D.recvbuf.p);   // scratch (everything before is synchronised)
+      CU(cudaMemcpyAsync(d_mine, offs, sizeof offs, cudaMemcpyHostToDevice, h->stream));
+      bool any = false;
+      for (int r : D.nbr_rank) if (r != D.rank) any = true;
+      if (any) NC(D.nccl->GroupStart());
+      for (int k = 0; k < nnb; k++) {
+        if (D.nbr_rank[k] == D.rank) {
+          CU(cudaMemcpyAsync(P.d_off.p + k, d_mine + k, sizeof(long long), cudaMemcpyDeviceToDevice, h->stream));
+          CU(cudaMemcpyAsync(P.d_off.p + 32 + k, d_mine + 32 + k, sizeof(long long), cudaMemcpyDeviceToDevice, h->stream));
+        } else {
+          NC(D.nccl->Send(d_mine + k, 1, ncclInt64, D.nbr_rank[k], D.comm, h->stream));
+          NC(D.nccl->Send(d_mine + 32 + k, 1, ncclInt64, D.nbr_rank[k], D.comm, h->stream));
+          NC(D.nccl->Recv(P.d_off.p + k, 1, ncclInt64, D.nbr_rank[k], D.comm, h->stream));
+          NC(D.nccl->Recv(P.d_off.p + 32 + k, 1, ncclInt64, D.nbr_rank[k], D.comm, h->stream));
+        }
+      }
+      if (any) NC(D.nccl->GroupEnd());
+      CU(cudaMemcpyAsync(D.h_off, P.d_off.p, 64 * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+    }
+  }
   // capacity for the ghosts
   if (nown + nghost + 32 > h->stride) {
     const int st2 = (int)(((int64_t)(nown + nghost) * 5 / 4 + 31) / 32 * 32) + 64;
@@ -328,7 +449,7 @@ int dd_borders(sh_ctx *h) {
   } catch (std::string &e) { return fail(h, e); }
   if (nsend > 0) {
     dd_order_kernel<<<cdiv((int64_t)nslot * nown, 256), 256, 0, h->stream>>>((size_t)nslot * nown, nown, D.flag.p, D.pos.p, D.send_idx.p, D.send_slot.p);
-    dd_pack_kernel<<<cdiv(nsend, 256), 256, 0, h->stream>>>(A, h->d_tag.p, G, nsend, D.send_idx.p, D.send_slot.p, 1, D.ghost_vel, D.sendbuf.p);
+    dd_pack_kernel<<<cdiv(nsend, 256), 256, 0, h->stream>>>(A, h->d_tag.p, G, nsend, D.send_idx.p, D.send_slot.p, 1, D.ghost_vel, D.sendbuf.p, PeerPlan{});
     h->kernel_launches += 2;
   }
   if ((rc2 = dd_sendrecv(h, D.nbr_rank, D.sendbuf.p, D.send_cnt, D.recvbuf.p, D.recv_cnt, wf))) return rc2;
@@ -356,21 +477,58 @@ int dd_borders(sh_ctx *h) {
   return 0;
 }
 
+// where this rank's records go in every neighbour's inbox (forward: my send list -> their F inbox; reverse: their ghosts
+// here, ordered by source -> their R inbox)
+void dd_peer_plan(sh_ctx *h, bool reverse, int parity, PeerPlan &plan) {
+  DdCtx &D = h->dd;
+  PeerCtx &P = D.peer;
+  const int nnb = (int)D.nbr_rank.size();
+  plan.enabled = 1; plan.nnbr = nnb;
+  int start = 0;
+  for (int k = 0; k < nnb; k++) {
+    plan.dst[k] = peer_inbox(P, P.base[k], P.pcapF[k], P.pcapR[k], reverse, parity, P.wmax);
+    plan.off[k] = D.h_off[(reverse ? 32 : 0) + k];
+    plan.seg_start[k] = start;
+    start += reverse ? D.recv_cnt[k] : D.send_cnt[k];
+    for (int s2 = D.slot_lo[k]; s2 < D.slot_hi[k]; s2++) plan.nbr_of_slot[s2] = k;
+  }
+}
+int dd_peer_sync(sh_ctx *h, bool reverse) {
+  DdCtx &D = h->dd;
+  PeerCtx &P = D.peer;
+  PeerSync S{};
+  const int nnb = (int)D.nbr_rank.size();
+  S.nnbr = nnb; S.myrank = D.rank;
+  for (int k = 0; k < nnb; k++) { S.peer_flags[k] = peer_flags(P.base[k], P.pcapF[k], P.pcapR[k], reverse, P.wmax); S.src_rank[k] = D.nbr_rank[k]; }
+  dd_peer_sync_kernel<<<1, 32, 0, h->stream>>>(S, peer_flags(P.region, P.capF, P.capR, reverse, P.wmax), reverse ? P.seq_r : P.seq_f, P.d_err);
+  h->kernel_launches++;
+  return 0;
+}
+
 // forward_comm: ghost x / quat (and v, angmom when a velocity-dependent contact model is on) every step; no host sync
 int dd_forward(sh_ctx *h) {
   DdCtx &D = h->dd;
-  if (D.nsend == 0 && h->nghost == 0) return 0;
+  if (!D.peer.enabled && D.nsend == 0 && h->nghost == 0) return 0;   // (peer path: the neighbours still wait for this rank's flag)
   dd_refresh_shifts(h);
   const int w = dd_width(h, false), nown = (int)(h->n - h->nghost);
   if (ev_tick(h, 6)) return -2;
+  PeerPlan plan{};
+  const double *src = D.recvbuf.p;
+  if (D.peer.enabled) {
+    PeerCtx &P = D.peer;
+    P.seq_f++;
+    dd_peer_plan(h, false, (int)(P.seq_f & 1), plan);
+    src = peer_inbox(P, P.region, P.capF, P.capR, false, (int)(P.seq_f & 1), P.wmax);
+  }
   if (D.nsend > 0) {
-    dd_pack_kernel<<<cdiv(D.nsend, 256), 256, 0, h->stream>>>(view(h), h->d_tag.p, D.G, D.nsend, D.send_idx.p, D.send_slot.p, 0, D.ghost_vel, D.sendbuf.p);
+    dd_pack_kernel<<<cdiv(D.nsend, 256), 256, 0, h->stream>>>(view(h), h->d_tag.p, D.G, D.nsend, D.send_idx.p, D.send_slot.p, 0, D.ghost_vel, D.sendbuf.p, plan);
     h->kernel_launches++;
   }
   int rc2;
-  if ((rc2 = dd_sendrecv(h, D.nbr_rank, D.sendbuf.p, D.send_cnt, D.recvbuf.p, D.recv_cnt, w))) return rc2;
+  if (D.peer.enabled) { if ((rc2 = dd_peer_sync(h, false))) return rc2; }
+  else if ((rc2 = dd_sendrecv(h, D.nbr_rank, D.sendbuf.p, D.send_cnt, D.recvbuf.p, D.recv_cnt, w))) return rc2;
   if (h->nghost > 0) {
-    dd_unpack_kernel<<<cdiv(h->nghost, 256), 256, 0, h->stream>>>(view_all(h), h->d_tag.p, nown, (int)h->nghost, 0, D.ghost_vel, D.recvbuf.p);
+    dd_unpack_kernel<<<cdiv(h->nghost, 256), 256, 0, h->stream>>>(view_all(h), h->d_tag.p, nown, (int)h->nghost, 0, D.ghost_vel, src);
     h->kernel_launches++;
   }
   ev_tock(h);
@@ -380,19 +538,28 @@ int dd_forward(sh_ctx *h) {
 // reverse_comm (newton on): f / torque gathered on the ghosts return to their owners and are added in a fixed order
 int dd_reverse(sh_ctx *h) {
   DdCtx &D = h->dd;
-  if (D.nsend == 0 && h->nghost == 0) return 0;
+  if (!D.peer.enabled && D.nsend == 0 && h->nghost == 0) return 0;
   const int nown = (int)(h->n - h->nghost), ng = (int)h->nghost;
   if (ev_tick(h, 6)) return -2;
   try { D.sendbuf.ensure((size_t)6 * std::max(ng, 1)); D.recvbuf.ensure((size_t)6 * std::max(D.nsend, 1)); }
   catch (std::string &e) { return fail(h, e); }
+  PeerPlan plan{};
+  const double *src = D.recvbuf.p;
+  if (D.peer.enabled) {
+    PeerCtx &P = D.peer;
+    P.seq_r++;
+    dd_peer_plan(h, true, (int)(P.seq_r & 1), plan);
+    src = peer_inbox(P, P.region, P.capF, P.capR, true, (int)(P.seq_r & 1), P.wmax);
+  }
   if (ng > 0) {
-    dd_pack_ghost_forces_kernel<<<cdiv(ng, 256), 256, 0, h->stream>>>(view_all(h), nown, ng, D.sendbuf.p);
+    dd_pack_ghost_forces_kernel<<<cdiv(ng, 256), 256, 0, h->stream>>>(view_all(h), nown, ng, D.sendbuf.p, plan);
     h->kernel_launches++;
   }
   int rc2;
-  if ((rc2 = dd_sendrecv(h, D.nbr_rank, D.sendbuf.p, D.recv_cnt, D.recvbuf.p, D.send_cnt, 6))) return rc2;
+  if (D.peer.enabled) { if ((rc2 = dd_peer_sync(h, true))) return rc2; }
+  else if ((rc2 = dd_sendrecv(h, D.nbr_rank, D.sendbuf.p, D.recv_cnt, D.recvbuf.p, D.send_cnt, 6))) return rc2;
   if (D.nsend > 0 && nown > 0) {
-    dd_add_returned_forces_kernel<<<cdiv(nown, 256), 256, 0, h->stream>>>(view(h), D.rev_off.p, D.rev_k.p, D.recvbuf.p);
+    dd_add_returned_forces_kernel<<<cdiv(nown, 256), 256, 0, h->stream>>>(view(h), D.rev_off.p, D.rev_k.p, src);
     h->kernel_launches++;
   }
   ev_tock(h);

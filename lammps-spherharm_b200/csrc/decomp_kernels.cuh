@@ -145,15 +145,29 @@ __global__ void dd_border_flag_kernel(AtomView A, DdGeom G, int *flag) {
   }
 }
 
+// destination of the per-step records when the exchange goes through peer memory: record k of the send list (which belongs to
+// neighbour nbr_of_slot[slot]) lands in that neighbour's inbox at its offset for this rank
+struct PeerPlan {
+  int enabled, nnbr;
+  double *dst[32];            // neighbour's inbox for this parity
+  long long off[32];          // my record offset inside it (records)
+  int seg_start[32];          // first send-list index of the neighbour's segment
+  int nbr_of_slot[26];
+};
+
 // ghost records.  border records (full = 1): tag, shape, then the per-step part; per-step part: x + shift, quat
 // [, v + vshift, angmom when with_vel]
 __global__ void dd_pack_kernel(AtomView A, const long long *tag, DdGeom G, int m, const int *send_idx, const int *send_slot,
-                               int full, int with_vel, double *out) {
+                               int full, int with_vel, double *out, const __grid_constant__ PeerPlan P) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= m) return;
   const int i = send_idx[k], s = send_slot[k], st = A.stride;
   const int w = (full ? 2 : 0) + 7 + (with_vel ? 6 : 0);
   double *o = out + (size_t)w * k;
+  if (P.enabled) {            // fused pack + push: the record is stored straight into the neighbour's memory over NVLink
+    const int nb = P.nbr_of_slot[s];
+    o = P.dst[nb] + (size_t)w * (size_t)(P.off[nb] + (k - P.seg_start[nb]));
+  }
   int b = 0;
   if (full) { o[0] = (double)tag[i]; o[1] = (double)A.shape[i]; b = 2; }
 #pragma unroll
@@ -204,12 +218,36 @@ __global__ void dd_rev_fill_kernel(int nown, int nslot, const int *flag, const i
   int e = rev_off[a];
   for (int s = 0; s < nslot; s++) if (flag[(size_t)s * nown + a]) rev_k[e++] = pos[(size_t)s * nown + a];
 }
-__global__ void dd_pack_ghost_forces_kernel(AtomView A, int first, int m, double *out) {
+__global__ void dd_pack_ghost_forces_kernel(AtomView A, int first, int m, double *out, const __grid_constant__ PeerPlan P) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= m) return;
   const int i = first + k, st = A.stride;
+  double *o = out + 6 * (size_t)k;
+  if (P.enabled) {            // ghost k came from neighbour nb (ghosts are ordered by source): return it to that rank's R inbox
+    int nb = 0;
+    while (nb + 1 < P.nnbr && k >= P.seg_start[nb + 1]) nb++;
+    o = P.dst[nb] + 6 * (size_t)(P.off[nb] + (k - P.seg_start[nb]));
+  }
 #pragma unroll
-  for (int d = 0; d < 3; d++) { out[6 * (size_t)k + d] = A.f[d * st + i]; out[6 * (size_t)k + 3 + d] = A.tq[d * st + i]; }
+  for (int d = 0; d < 3; d++) { o[d] = A.f[d * st + i]; o[3 + d] = A.tq[d * st + i]; }
+}
+// publish "my push number `seq` is complete" to every neighbour, then wait until every neighbour has published the same.
+// Launched after the pack kernel on the same stream: its stores are complete (and visible system-wide) when this starts.
+// flag rows are indexed by the WRITER's rank.  A wait that lasts longer than ~4 s raises *err instead of hanging the GPU.
+struct PeerSync { int nnbr, myrank; unsigned long long *peer_flags[32]; int src_rank[32]; };
+__global__ void dd_peer_sync_kernel(const __grid_constant__ PeerSync S, unsigned long long *my_flags, unsigned long long seq, int *err) {
+  const int k = threadIdx.x;
+  if (k >= S.nnbr) return;
+  __threadfence_system();
+  *(volatile unsigned long long *)&S.peer_flags[k][S.myrank] = seq;
+  __threadfence_system();
+  volatile unsigned long long *f = my_flags + S.src_rank[k];
+  const long long t0 = clock64();
+  while (*f < seq) {
+    if (clock64() - t0 > 8000000000LL) { atomicExch(err, 1); break; }
+    __nanosleep(100);
+  }
+  __threadfence_system();
 }
 // fixed order per atom (ascending slot): bitwise reproducible
 __global__ void dd_add_returned_forces_kernel(AtomView A, const int *rev_off, const int *rev_k, const double *in) {

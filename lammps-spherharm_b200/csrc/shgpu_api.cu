@@ -677,7 +677,7 @@ int run_split_pipeline(sh_ctx *h, PairArgs &P) {
 
 int compute_forces_device(sh_ctx *h) {
   const int n = (int)(h->n - h->nghost);   // forces are accumulated on owned atoms only
-  const bool newton_dd = h->dd.on && h->dd.newton && h->dd.borders_ok && h->dd.nranks >= 1 && (h->nghost > 0 || h->dd.nsend > 0);
+  const bool newton_dd = h->dd.on && h->dd.newton && h->dd.borders_ok && (h->dd.peer.enabled || h->nghost > 0 || h->dd.nsend > 0);
   if (n == 0 && !newton_dd) { h->forces_valid = true; return 0; }
   AtomView A = view(h);
   const int nb = std::max(1, cdiv(n, 256));
@@ -870,6 +870,9 @@ int sh_destroy(sh_ctx *h) {
   if (h->dd.h_int) cudaFreeHost(h->dd.h_int);
   for (auto &e : h->ev_lag) if (e) cudaEventDestroy(e);
   for (auto &e : h->ev_step) cudaEventDestroy(e);
+  dd_peer_release(h);
+  if (h->dd.peer.d_err) cudaFree(h->dd.peer.d_err);
+  h->dd.peer.d_off.release();
   if (h->dd.comm && h->dd.nccl) h->dd.nccl->CommDestroy(h->dd.comm);
   {
     DdCtx &D = h->dd;
@@ -1250,6 +1253,7 @@ int sh_run(sh_ctx *h, int64_t nsteps) try {
     }
   }
   CU(cudaMemcpyAsync(h->h_lagflag + 2, h->scalars.p + 6, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (h->dd.peer.d_err) CU(cudaMemcpyAsync(h->h_lagflag + 3, h->dd.peer.d_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaEventRecord(h->run_e1, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaGetLastError());
@@ -1259,6 +1263,7 @@ int sh_run(sh_ctx *h, int64_t nsteps) try {
     for (int64_t k = 0; k < nsteps; k++) cudaEventElapsedTime(&h->step_ms[k], h->ev_step[k], h->ev_step[k + 1]);
     h->step_flags_last = h->step_flags;
   } else h->step_ms.clear();
+  if (h->dd.peer.d_err && h->h_lagflag[3] != 0) return fail(h, "ghost exchange over peer memory timed out waiting for a neighbour rank");
   if (h->h_lagflag[2] != 0) {
     CU(cudaMemset(h->scalars.p + 6, 0, sizeof(int)));
     return fail(h, "neighbor skin violated: an atom moved more than half the skin on a step the lagged neighbor decision did not "
@@ -1648,7 +1653,8 @@ int sh_set_tuning(sh_ctx *h, const char *key, double value) try {
     if (!h->shapes.empty()) return fail(h, "cube_n must be set before add_shape");
     if (v != 0 && (v < 8 || v > 144)) return fail(h, "cube_n must be 0 (default) or 8..144");
     h->cube_n = v;
-  } else if (k == "newton") { h->dd.newton = v != 0; h->list_valid = false; h->forces_valid = false; }
+  } else if (k == "peer_exchange") { h->dd.peer.want = v != 0; if (!h->dd.peer.want && h->dd.peer.enabled) return fail(h, "peer_exchange can only be switched off before the first run"); }
+  else if (k == "newton") { h->dd.newton = v != 0; h->list_valid = false; h->forces_valid = false; }
   else if (k == "step_trace") { h->step_trace = v != 0; }
   else if (k == "dd_self_ghosts") { h->dd.self_ghosts = v != 0; h->dd.geometry_ok = false; h->dd.borders_ok = false; }
   else if (k == "sync_rebuild") { h->lag_mode = v == 0; h->lag_pending = false; }
