@@ -837,7 +837,8 @@ __device__ __forceinline__ void add_node(NodeSums &a, const double *__restrict__
   a.n++;
 }
 
-__global__ void __launch_bounds__(128, 6) pair_reduce_kernel(PairArgs A, SplitArgs S) {
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) pair_reduce_kernel(PairArgs A, SplitArgs S) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   int c_pairs = 0, c_trans = 0, c_inside = 0, c_ghost = 0;
   if (p < A.npairs) {

@@ -115,6 +115,7 @@ struct sh_ctx {
   int64_t cache_age = 0;                       // pair phases since the last cache build
   bool cache_exhausted = false;                // the last invalidation came from the displacement margin
   int cube_n = 0;                              // direction cells per cube-face edge (0 = default)
+  int reduce_occ = 0;
   int eval_pts = 0, eval_occ = 0, eval_mode = 0;   // pair_eval_kernel: points per lane, min CTAs/SM, 1 = one block per CTA
   long long last_records = 0;                  // records of the previous pair phase (advisory)
   // candidate cache
@@ -655,7 +656,9 @@ int run_split_pipeline(sh_ctx *h, PairArgs &P) {
   h->eval_launches++;
   // ---- C
   if (tick(2)) return -2;
-  pair_reduce_kernel<<<cdiv(np, 128), 128, 0, h->stream>>>(P, S);
+  if (h->reduce_occ == 4) pair_reduce_kernel<4><<<cdiv(np, 128), 128, 0, h->stream>>>(P, S);
+  else if (h->reduce_occ == 8) pair_reduce_kernel<8><<<cdiv(np, 128), 128, 0, h->stream>>>(P, S);
+  else pair_reduce_kernel<6><<<cdiv(np, 128), 128, 0, h->stream>>>(P, S);
   tock();
   h->kernel_launches++;
   // ---- deep contacts / pairs that found the pool full: fused kernel over the device-side list
@@ -1645,6 +1648,7 @@ int sh_set_tuning(sh_ctx *h, const char *key, double value) try {
   const int v = (int)value;
   if (k == "cull_wpb") { if (v != 0 && v != 1 && v != 2 && v != 4 && v != 8) return fail(h, "cull_wpb must be 0, 1, 2, 4 or 8"); h->tune_cull_wpb = v; }
   else if (k == "cull_lpp") { if (v != 0 && v != 16 && v != 32) return fail(h, "cull_lpp must be 0, 16 or 32"); h->tune_cull_lpp = v; }
+  else if (k == "reduce_occ") { if (v != 0 && v != 4 && v != 6 && v != 8) return fail(h, "reduce_occ must be 0, 4, 6 or 8"); h->reduce_occ = v; }
   else if (k == "eval_pts") { if (v != 0 && v != 2 && v != 4) return fail(h, "eval_pts must be 0, 2 or 4"); h->eval_pts = v; }
   else if (k == "eval_occ") { if (v != 0 && v != 3 && v != 4) return fail(h, "eval_occ must be 0, 3 or 4"); h->eval_occ = v; }
   else if (k == "eval_mode") { if (v < 0 || v > 2) return fail(h, "eval_mode must be 0 (default), 1 (one block per CTA) or 2 (persistent chunks)"); h->eval_mode = v; }
