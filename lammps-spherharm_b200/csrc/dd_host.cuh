@@ -223,6 +223,16 @@ int dd_peer_setup(sh_ctx *h, long long needF, long long needR) {
   DdCtx &D = h->dd;
   PeerCtx &P = D.peer;
   CU(cudaStreamSynchronize(h->stream));
+  if (P.region) {
+    // growing an existing region: every rank first lets go of its neighbours' regions, and only when ALL have done so does
+    // anybody free its own (an exporter must not free memory that an importer still has mapped)
+    for (void *q : P.opened) cudaIpcCloseMemHandle(q);
+    P.opened.clear();
+    int *d_bar = h->dd.d_int.p + 251;
+    CU(cudaMemsetAsync(d_bar, 0, sizeof(int), h->stream));
+    NC(D.nccl->AllReduce(d_bar, d_bar, 1, ncclInt, ncclMax, D.comm, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
   dd_peer_release(h);
   P.capF = std::max<long long>(4096, 2 * needF); P.capR = std::max<long long>(4096, 2 * needR);
   const size_t nd = (size_t)2 * P.capF * P.wmax + (size_t)2 * P.capR * 6 + 2 * DD_MAX_RANKS;
