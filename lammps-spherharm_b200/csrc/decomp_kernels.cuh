@@ -233,7 +233,7 @@ __global__ void dd_pack_ghost_forces_kernel(AtomView A, int first, int m, double
 }
 // publish "my push number `seq` is complete" to every neighbour, then wait until every neighbour has published the same.
 // Launched after the pack kernel on the same stream: its stores are complete (and visible system-wide) when this starts.
-// flag rows are indexed by the WRITER's rank.  A wait that lasts longer than ~4 s raises *err instead of hanging the GPU.
+// flag rows are indexed by the WRITER's rank.  A wait that lasts longer than ~10 s raises *err instead of hanging the GPU.
 struct PeerSync { int nnbr, myrank; unsigned long long *peer_flags[32]; int src_rank[32]; };
 __global__ void dd_peer_sync_kernel(const __grid_constant__ PeerSync S, unsigned long long *my_flags, unsigned long long seq, int *err) {
   const int k = threadIdx.x;
@@ -244,7 +244,9 @@ __global__ void dd_peer_sync_kernel(const __grid_constant__ PeerSync S, unsigned
   volatile unsigned long long *f = my_flags + S.src_rank[k];
   const long long t0 = clock64();
   while (*f < seq) {
-    if (clock64() - t0 > 8000000000LL) { atomicExch(err, 1); break; }
+    // ~10 s at 2 GHz; once a wait has failed no later one spins again (the run ends with an error, not with a long hang)
+    if (*(volatile int *)err != 0) break;
+    if (clock64() - t0 > 20000000000LL) { atomicExch(err, 1); break; }
     __nanosleep(100);
   }
   __threadfence_system();
